@@ -1,0 +1,42 @@
+// Host-side interface of the tcgen05 GEMM used by every Linear layer on the path.
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+
+namespace fmmt {
+
+enum Act : int { ACT_NONE = 0, ACT_GELU = 1, ACT_RELU = 2, ACT_TANH = 3 };
+
+// out[dest(r), n] = act( sum_k A[r,k] * W[n,k] + bias[n] ) + residual[dest(r), n]
+//   A  : bf16 row-major [M, lda]  (K contiguous)      -> "x" of nn.Linear
+//   W  : bf16 row-major [N, ldw]  (K contiguous)      -> nn.Linear.weight as stored by the reference
+// dest(r): optional row remap so that producers can run in window order and scatter back
+//   (Swin window_reverse + roll, Swin_Transformer.py:258-264) or write into a slice of a concat buffer.
+struct GemmArgs {
+  const __nv_bfloat16* A = nullptr;
+  int lda = 0;
+  const __nv_bfloat16* W = nullptr;
+  int ldw = 0;
+  int M = 0, N = 0, K = 0;
+  const float* bias = nullptr;      // [N] fp32
+  int act = ACT_NONE;
+  const float* residual = nullptr;  // fp32 [*, ldr], indexed by dest row
+  int ldr = 0;
+  float* out_f32 = nullptr;         // fp32 [*, ldo32], indexed by dest row
+  int ldo32 = 0;
+  __nv_bfloat16* out_bf16 = nullptr;  // bf16 [*, ldo16], indexed by dest row
+  int ldo16 = 0;
+  const int* row_map = nullptr;     // dest = (r / map_period) * map_period + row_map[r % map_period]
+  int map_period = 0;
+  int rows_in = 0, rows_out = 0, row_off = 0;  // if rows_in>0: dest = (r/rows_in)*rows_out + row_off + r%rows_in
+  int block_n = 0;                  // 0 = choose automatically
+};
+
+// Returns cudaSuccess or the launch / tensor-map error. Asynchronous on `stream`.
+cudaError_t launch_gemm(const GemmArgs& a, cudaStream_t stream);
+
+// Algorithmic work of one launch (2*M*N*K) for roofline accounting.
+inline double gemm_flops(const GemmArgs& a) { return 2.0 * a.M * (double)a.N * a.K; }
+
+}  // namespace fmmt

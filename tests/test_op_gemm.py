@@ -1,0 +1,96 @@
+"""Parity of the tcgen05 GEMM (fmmt_op_gemm, C ABI) against a plain fp32 torch matmul of the same bf16 operands.
+
+Tolerance: operands are identical bf16 values on both sides, accumulation is fp32 on both -> only summation order
+differs: |err| <= 2e-3 * sqrt(K)/16 on O(1) data; bf16 outputs add one rounding (rel 2^-8).
+"""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _run(lib, M, N, K, bias=False, act=0, residual=False, out16=False, row_map=False, block_n=0, lda_pad=0):
+    from facialmmt_b200._lib import check, cur_stream, ptr
+    g = torch.Generator(device="cpu").manual_seed(M * 7919 + N * 31 + K)
+    lda = K + lda_pad
+    lda = (lda + 7) // 8 * 8
+    A = torch.zeros(M, lda, dtype=torch.bfloat16)
+    A[:, :K] = torch.randn(M, K, generator=g).to(torch.bfloat16)
+    W = torch.zeros(N, lda, dtype=torch.bfloat16)
+    W[:, :K] = (torch.randn(N, K, generator=g) / K ** 0.5).to(torch.bfloat16)
+    b = torch.randn(N, generator=g) if bias else None
+    R = torch.randn(M, N, generator=g) if residual else None
+    rm = None
+    period = 0
+    if row_map:
+        period = 49 if M % 49 == 0 else M
+        rm = torch.randperm(period, generator=g).to(torch.int32)
+    dev = "cuda"
+    Ad, Wd = A.to(dev), W.to(dev)
+    bd = b.to(dev) if bias else None
+    Rd = R.to(dev) if residual else None
+    rmd = rm.to(dev) if row_map else None
+    o32 = torch.full((M, N), float("nan"), device=dev, dtype=torch.float32)
+    o16 = torch.zeros(M, N, device=dev, dtype=torch.bfloat16) if out16 else None
+    check(lib.fmmt_op_gemm(ptr(Ad), lda, ptr(Wd), lda, M, N, K, ptr(bd), act, ptr(Rd), N, ptr(o32), N,
+                           ptr(o16), N, ptr(rmd), period, block_n, cur_stream()), "fmmt_op_gemm")
+    torch.cuda.synchronize()
+    ref = A[:, :K].float() @ W[:, :K].float().t()
+    if bias:
+        ref = ref + b
+    if act == 1:
+        ref = torch.nn.functional.gelu(ref)
+    elif act == 2:
+        ref = torch.relu(ref)
+    elif act == 3:
+        ref = torch.tanh(ref)
+    if row_map:
+        idx = (torch.arange(M) // period) * period + rm.long()[torch.arange(M) % period]
+        full = torch.empty_like(ref)
+        full[idx] = ref
+        ref = full
+    if residual:
+        ref = ref + R
+    got = o32.cpu()
+    assert torch.isfinite(got).all(), "unwritten outputs"
+    err = (got - ref).abs().max().item()
+    tol = 2e-3 * max(1.0, (K ** 0.5) / 16)
+    assert err < tol, f"fp32 out max err {err} (tol {tol}) M={M} N={N} K={K}"
+    if out16:
+        err16 = (o16.float().cpu() - ref).abs().max().item()
+        assert err16 < tol + 0.02 * ref.abs().max().item()
+    return err
+
+
+@pytest.mark.parametrize("M,N,K", [
+    (128, 96, 96), (256, 288, 96), (3136, 96, 384), (784 * 2, 576, 192), (196 * 3, 1152, 384),
+    (49 * 5, 2304, 768), (49 * 5, 768, 3072), (100, 512, 37632), (8 * 128, 3072, 1024), (1000, 1024, 4096),
+    (77, 768, 519), (130, 96, 48), (1, 768, 768), (3136 * 8, 384, 96),
+])
+def test_gemm_shapes(lib, M, N, K):
+    _run(lib, M, N, K)
+
+
+@pytest.mark.parametrize("bn", [32, 64, 96, 128, 192, 256])
+def test_gemm_block_n(lib, bn):
+    _run(lib, 500, 768, 320, block_n=bn, bias=True)
+
+
+def test_gemm_epilogues(lib):
+    _run(lib, 49 * 16, 384, 384, bias=True, act=1, out16=True)
+    _run(lib, 49 * 16, 384, 384, bias=True, residual=True, row_map=True)
+    _run(lib, 49 * 16, 96, 96, bias=True, residual=True, row_map=True, out16=True)
+    _run(lib, 300, 768, 768, bias=True, act=3)
+    _run(lib, 300, 64, 512, bias=True, act=2)
+    _run(lib, 300, 40, 128, bias=True)  # ragged N (scalar tail)
+
+
+def test_gemm_rejects_bad_alignment(lib):
+    from facialmmt_b200._lib import cur_stream, ptr
+    A = torch.zeros(8, 12, dtype=torch.bfloat16, device="cuda")
+    W = torch.zeros(8, 12, dtype=torch.bfloat16, device="cuda")
+    o = torch.zeros(8, 8, device="cuda")
+    rc = lib.fmmt_op_gemm(ptr(A), 12, ptr(W), 12, 8, 8, 12, None, 0, None, 0, ptr(o), 8, None, 0, None, 0, 0,
+                          cur_stream())
+    assert rc != 0
+    assert b"invalid" in lib.fmmt_last_error()
