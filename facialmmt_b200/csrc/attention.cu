@@ -1,0 +1,348 @@
+// Attention cores of the path (bf16 operands, fp32 softmax, warp-shuffle row reductions):
+//   * window_attention_kernel : Swin W-MSA / SW-MSA core, N = ws*ws (49) tokens, head_dim 32,
+//       softmax(q*scale @ k^T + rel_bias[h] (+ shift mask)) @ v      (Swin_Transformer.py:119-141)
+//   * mha_flash_kernel        : head_dim 64 attention with online softmax over 64-key tiles, optional additive key
+//       mask (1-m)*neg: HF text encoder, MELDTrans SelfAttention (Transformer.py:87-116), fairseq-style
+//       MultiheadAttention core (multihead_attention.py:109-130, no masks).
+// Tensor-core path here is mma.sync.m16n8k16 (tiles are 49x49x32 / 64x64x64: too small to amortise a
+// TMEM round trip); the large GEMMs around them run on tcgen05 (gemm.cu).
+#include "ops.cuh"
+#include "ptx.cuh"
+
+namespace fmmt {
+
+namespace {
+
+__device__ __forceinline__ void ldmatrix_x4(uint32_t (&r)[4], const void* smem_ptr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(smem_u32(smem_ptr)));
+}
+__device__ __forceinline__ void ldmatrix_x4_trans(uint32_t (&r)[4], const void* smem_ptr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(smem_u32(smem_ptr)));
+}
+// D(16x8,f32) += A(16x16,bf16,row) * B(16x8,bf16,col)
+__device__ __forceinline__ void mma_bf16(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+// ------------------------------------------------------------------------------------------ Swin window attention
+constexpr int WA_D = 32;        // head_dim (all four Swin-tiny stages)
+constexpr int WA_PITCH = 40;    // smem row pitch in bf16 (80 B): conflict-free ldmatrix
+constexpr int WA_ROWS = 64;     // 49 tokens padded to 4 m-tiles
+constexpr int WA_NT = 7;        // key n-tiles (56 >= 49)
+
+struct WinAttnParams {
+  const __nv_bfloat16* qkv;  // [num_windows*N, 3C], window order; q | k | v blocks of C, head h at h*32
+  __nv_bfloat16* out;        // [num_windows*N, C]
+  const float* bias;         // [heads, N, N] expanded relative-position bias
+  const int8_t* rid;         // [nW, N] shift-region ids or nullptr (no mask)
+  int num_windows, nW, heads, C, N;
+  float scale;
+};
+
+__global__ void __launch_bounds__(128) window_attention_kernel(const WinAttnParams p) {
+  __shared__ __align__(16) __nv_bfloat16 sQ[WA_ROWS * WA_PITCH];
+  __shared__ __align__(16) __nv_bfloat16 sK[WA_ROWS * WA_PITCH];
+  __shared__ __align__(16) __nv_bfloat16 sV[WA_ROWS * WA_PITCH];
+  __shared__ int8_t sRid[WA_ROWS];
+
+  const int wb = blockIdx.x;   // window index over the whole batch
+  const int h = blockIdx.y;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int N = p.N;
+  const int ld = 3 * p.C;
+
+  // stage q, k, v (rows >= N zero-filled): 3 matrices x 64 rows x 4 chunks of 16 B
+  for (int idx = tid; idx < 3 * WA_ROWS * 4; idx += 128) {
+    const int mat = idx / (WA_ROWS * 4);
+    const int rem = idx - mat * (WA_ROWS * 4);
+    const int row = rem >> 2, ch = rem & 3;
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (row < N)
+      v = *reinterpret_cast<const uint4*>(p.qkv + (static_cast<size_t>(wb) * N + row) * ld + mat * p.C + h * WA_D +
+                                          ch * 8);
+    __nv_bfloat16* dst = (mat == 0 ? sQ : (mat == 1 ? sK : sV)) + row * WA_PITCH + ch * 8;
+    *reinterpret_cast<uint4*>(dst) = v;
+  }
+  if (tid < WA_ROWS) sRid[tid] = (p.rid != nullptr && tid < N) ? p.rid[(wb % p.nW) * N + tid] : 0;
+  __syncthreads();
+
+  const int r0 = warp * 16 + (lane >> 2);  // this thread's rows: r0 and r0 + 8
+  const int cq = (lane & 3) * 2;
+
+  // S = Q K^T  (16 x 56 per warp)
+  float s[WA_NT][4];
+#pragma unroll
+  for (int j = 0; j < WA_NT; ++j) s[j][0] = s[j][1] = s[j][2] = s[j][3] = 0.f;
+#pragma unroll
+  for (int kk = 0; kk < WA_D / 16; ++kk) {
+    uint32_t a[4];
+    ldmatrix_x4(a, sQ + (warp * 16 + (lane & 15)) * WA_PITCH + kk * 16 + (lane >> 4) * 8);
+#pragma unroll
+    for (int jp = 0; jp < 4; ++jp) {  // key n-tile pairs (0,1) (2,3) (4,5) (6,7); tile 7 is discarded
+      uint32_t b[4];
+      ldmatrix_x4(b, sK + (jp * 16 + (lane & 7) + (lane >> 4) * 8) * WA_PITCH + kk * 16 + ((lane >> 3) & 1) * 8);
+      mma_bf16(s[2 * jp], a, b[0], b[1]);
+      if (2 * jp + 1 < WA_NT) mma_bf16(s[2 * jp + 1 < WA_NT ? 2 * jp + 1 : 0], a, b[2], b[3]);
+    }
+  }
+
+  // scale, + relative position bias, + shift mask; keys >= N excluded
+  const float* bias_h = p.bias + static_cast<size_t>(h) * N * N;
+  const bool use_mask = p.rid != nullptr;
+  float mx[2] = {-INFINITY, -INFINITY};
+#pragma unroll
+  for (int j = 0; j < WA_NT; ++j) {
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int row = r0 + (e >> 1) * 8;
+      const int col = j * 8 + cq + (e & 1);
+      float v = -INFINITY;
+      if (col < N && row < N) {
+        v = s[j][e] * p.scale + __ldg(bias_h + row * N + col);
+        if (use_mask && sRid[row] != sRid[col]) v += -100.0f;
+      } else if (col < N) {
+        v = 0.f;  // padded query rows: keep finite, never stored
+      }
+      s[j][e] = v;
+      mx[e >> 1] = fmaxf(mx[e >> 1], v);
+    }
+  }
+  float sum[2] = {0.f, 0.f};
+#pragma unroll
+  for (int hh = 0; hh < 2; ++hh) {
+    mx[hh] = fmaxf(mx[hh], __shfl_xor_sync(0xffffffffu, mx[hh], 1));
+    mx[hh] = fmaxf(mx[hh], __shfl_xor_sync(0xffffffffu, mx[hh], 2));
+  }
+#pragma unroll
+  for (int j = 0; j < WA_NT; ++j) {
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float v = __expf(s[j][e] - mx[e >> 1]);
+      s[j][e] = v;
+      sum[e >> 1] += v;
+    }
+  }
+#pragma unroll
+  for (int hh = 0; hh < 2; ++hh) {
+    sum[hh] += __shfl_xor_sync(0xffffffffu, sum[hh], 1);
+    sum[hh] += __shfl_xor_sync(0xffffffffu, sum[hh], 2);
+  }
+
+  // O = P V  (16 x 32 per warp), P re-used from the S accumulators as bf16 A fragments
+  float o[4][4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) o[j][0] = o[j][1] = o[j][2] = o[j][3] = 0.f;
+#pragma unroll
+  for (int kk = 0; kk < 4; ++kk) {  // 16-key tiles; tile 3 = keys 48..63 (n-tile 6 + zeros)
+    uint32_t a[4];
+    a[0] = pack_bf16(s[2 * kk][0], s[2 * kk][1]);
+    a[1] = pack_bf16(s[2 * kk][2], s[2 * kk][3]);
+    if (2 * kk + 1 < WA_NT) {
+      a[2] = pack_bf16(s[(2 * kk + 1) % WA_NT][0], s[(2 * kk + 1) % WA_NT][1]);
+      a[3] = pack_bf16(s[(2 * kk + 1) % WA_NT][2], s[(2 * kk + 1) % WA_NT][3]);
+    } else {
+      a[2] = 0u;
+      a[3] = 0u;
+    }
+#pragma unroll
+    for (int np = 0; np < 2; ++np) {  // dim n-tile pairs (0,1), (2,3)
+      uint32_t b[4];
+      ldmatrix_x4_trans(b, sV + (kk * 16 + (lane & 7) + ((lane >> 3) & 1) * 8) * WA_PITCH + np * 16 + (lane >> 4) * 8);
+      mma_bf16(o[2 * np], a, b[0], b[1]);
+      mma_bf16(o[2 * np + 1], a, b[2], b[3]);
+    }
+  }
+  const float inv0 = 1.f / sum[0], inv1 = 1.f / sum[1];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int col = h * WA_D + j * 8 + cq;
+    if (r0 < N)
+      *reinterpret_cast<uint32_t*>(p.out + (static_cast<size_t>(wb) * N + r0) * p.C + col) =
+          pack_bf16(o[j][0] * inv0, o[j][1] * inv0);
+    if (r0 + 8 < N)
+      *reinterpret_cast<uint32_t*>(p.out + (static_cast<size_t>(wb) * N + r0 + 8) * p.C + col) =
+          pack_bf16(o[j][2] * inv1, o[j][3] * inv1);
+  }
+}
+
+// ------------------------------------------------------------------------------------------ general MHA (d = 64)
+constexpr int FA_D = 64;
+constexpr int FA_PITCH = 72;  // 144 B rows: conflict-free ldmatrix
+constexpr int FA_BQ = 64;
+constexpr int FA_BK = 64;
+
+struct MhaParams {
+  const __nv_bfloat16* q; int ldq;   // row (b*Lq + i), col h*64 + d
+  const __nv_bfloat16* k; int ldk;   // row (b*Lk + j)
+  const __nv_bfloat16* v; int ldv;
+  __nv_bfloat16* out; int ldo;       // row (b*Lq + i), col h*64 + d
+  const float* key_mask;             // [B, Lk] of 0/1 or nullptr
+  float mask_neg;                    // additive value for masked keys: (1 - m) * mask_neg
+  int B, H, Lq, Lk;
+  float scale;
+};
+
+__global__ void __launch_bounds__(128) mha_flash_kernel(const MhaParams p) {
+  __shared__ __align__(16) __nv_bfloat16 sQ[FA_BQ * FA_PITCH];
+  __shared__ __align__(16) __nv_bfloat16 sK[FA_BK * FA_PITCH];
+  __shared__ __align__(16) __nv_bfloat16 sV[FA_BK * FA_PITCH];
+  __shared__ float sMask[FA_BK];
+
+  const int q0 = blockIdx.x * FA_BQ;
+  const int h = blockIdx.y, b = blockIdx.z;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+  for (int idx = tid; idx < FA_BQ * 8; idx += 128) {
+    const int row = idx >> 3, ch = idx & 7;
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (q0 + row < p.Lq)
+      v = *reinterpret_cast<const uint4*>(p.q + (static_cast<size_t>(b) * p.Lq + q0 + row) * p.ldq + h * FA_D + ch * 8);
+    *reinterpret_cast<uint4*>(sQ + row * FA_PITCH + ch * 8) = v;
+  }
+  __syncthreads();
+  uint32_t qf[FA_D / 16][4];
+#pragma unroll
+  for (int kk = 0; kk < FA_D / 16; ++kk)
+    ldmatrix_x4(qf[kk], sQ + (warp * 16 + (lane & 15)) * FA_PITCH + kk * 16 + (lane >> 4) * 8);
+
+  float o[8][4];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) o[j][0] = o[j][1] = o[j][2] = o[j][3] = 0.f;
+  float m_run[2] = {-INFINITY, -INFINITY};
+  float l_run[2] = {0.f, 0.f};
+  const int cq = (lane & 3) * 2;
+
+  for (int k0 = 0; k0 < p.Lk; k0 += FA_BK) {
+    __syncthreads();  // previous tile fully consumed
+    for (int idx = tid; idx < 2 * FA_BK * 8; idx += 128) {
+      const int mat = idx / (FA_BK * 8);
+      const int rem = idx - mat * (FA_BK * 8);
+      const int row = rem >> 3, ch = rem & 7;
+      uint4 v = make_uint4(0, 0, 0, 0);
+      if (k0 + row < p.Lk) {
+        const __nv_bfloat16* src = mat == 0 ? p.k + (static_cast<size_t>(b) * p.Lk + k0 + row) * p.ldk
+                                            : p.v + (static_cast<size_t>(b) * p.Lk + k0 + row) * p.ldv;
+        v = *reinterpret_cast<const uint4*>(src + h * FA_D + ch * 8);
+      }
+      *reinterpret_cast<uint4*>((mat == 0 ? sK : sV) + row * FA_PITCH + ch * 8) = v;
+    }
+    if (tid < FA_BK) {
+      float add = 0.f;
+      if (k0 + tid >= p.Lk) add = -INFINITY;
+      else if (p.key_mask != nullptr) add = (1.0f - p.key_mask[static_cast<size_t>(b) * p.Lk + k0 + tid]) * p.mask_neg;
+      sMask[tid] = add;
+    }
+    __syncthreads();
+
+    float s[8][4];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s[j][0] = s[j][1] = s[j][2] = s[j][3] = 0.f;
+#pragma unroll
+    for (int kk = 0; kk < FA_D / 16; ++kk) {
+#pragma unroll
+      for (int jp = 0; jp < 4; ++jp) {
+        uint32_t bb[4];
+        ldmatrix_x4(bb, sK + (jp * 16 + (lane & 7) + (lane >> 4) * 8) * FA_PITCH + kk * 16 + ((lane >> 3) & 1) * 8);
+        mma_bf16(s[2 * jp], qf[kk], bb[0], bb[1]);
+        mma_bf16(s[2 * jp + 1], qf[kk], bb[2], bb[3]);
+      }
+    }
+    float mx[2] = {m_run[0], m_run[1]};
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float v = s[j][e] * p.scale + sMask[j * 8 + cq + (e & 1)];
+        s[j][e] = v;
+        mx[e >> 1] = fmaxf(mx[e >> 1], v);
+      }
+    }
+    float alpha[2], rs[2] = {0.f, 0.f};
+#pragma unroll
+    for (int hh = 0; hh < 2; ++hh) {
+      mx[hh] = fmaxf(mx[hh], __shfl_xor_sync(0xffffffffu, mx[hh], 1));
+      mx[hh] = fmaxf(mx[hh], __shfl_xor_sync(0xffffffffu, mx[hh], 2));
+      alpha[hh] = (m_run[hh] == -INFINITY) ? 0.f : __expf(m_run[hh] - mx[hh]);
+      m_run[hh] = mx[hh];
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float v = __expf(s[j][e] - mx[e >> 1]);
+        s[j][e] = v;
+        rs[e >> 1] += v;
+      }
+    }
+#pragma unroll
+    for (int hh = 0; hh < 2; ++hh) {
+      rs[hh] += __shfl_xor_sync(0xffffffffu, rs[hh], 1);
+      rs[hh] += __shfl_xor_sync(0xffffffffu, rs[hh], 2);
+      l_run[hh] = l_run[hh] * alpha[hh] + rs[hh];
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      o[j][0] *= alpha[0]; o[j][1] *= alpha[0];
+      o[j][2] *= alpha[1]; o[j][3] *= alpha[1];
+    }
+#pragma unroll
+    for (int kk = 0; kk < FA_BK / 16; ++kk) {
+      uint32_t a[4];
+      a[0] = pack_bf16(s[2 * kk][0], s[2 * kk][1]);
+      a[1] = pack_bf16(s[2 * kk][2], s[2 * kk][3]);
+      a[2] = pack_bf16(s[2 * kk + 1][0], s[2 * kk + 1][1]);
+      a[3] = pack_bf16(s[2 * kk + 1][2], s[2 * kk + 1][3]);
+#pragma unroll
+      for (int np = 0; np < 4; ++np) {
+        uint32_t bb[4];
+        ldmatrix_x4_trans(bb, sV + (kk * 16 + (lane & 7) + ((lane >> 3) & 1) * 8) * FA_PITCH + np * 16 + (lane >> 4) * 8);
+        mma_bf16(o[2 * np], a, bb[0], bb[1]);
+        mma_bf16(o[2 * np + 1], a, bb[2], bb[3]);
+      }
+    }
+  }
+  const int r0 = q0 + warp * 16 + (lane >> 2);
+  const float inv0 = 1.f / l_run[0], inv1 = 1.f / l_run[1];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int col = h * FA_D + j * 8 + cq;
+    if (r0 < p.Lq)
+      *reinterpret_cast<uint32_t*>(p.out + (static_cast<size_t>(b) * p.Lq + r0) * p.ldo + col) =
+          pack_bf16(o[j][0] * inv0, o[j][1] * inv0);
+    if (r0 + 8 < p.Lq)
+      *reinterpret_cast<uint32_t*>(p.out + (static_cast<size_t>(b) * p.Lq + r0 + 8) * p.ldo + col) =
+          pack_bf16(o[j][2] * inv1, o[j][3] * inv1);
+  }
+}
+
+}  // namespace
+
+cudaError_t launch_window_attention(const __nv_bfloat16* qkv, __nv_bfloat16* out, const float* bias,
+                                    const int8_t* rid, int num_windows, int nW, int heads, int C, int N, float scale,
+                                    cudaStream_t stream) {
+  if (C != heads * WA_D || N > 49 || N < 1 || num_windows <= 0 || (C % 8) != 0) return cudaErrorInvalidValue;
+  WinAttnParams p{qkv, out, bias, rid, num_windows, nW, heads, C, N, scale};
+  dim3 grid(num_windows, heads);
+  window_attention_kernel<<<grid, 128, 0, stream>>>(p);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_mha(const __nv_bfloat16* q, int ldq, const __nv_bfloat16* k, int ldk, const __nv_bfloat16* v,
+                       int ldv, __nv_bfloat16* out, int ldo, const float* key_mask, float mask_neg, int B, int H,
+                       int Lq, int Lk, float scale, cudaStream_t stream) {
+  if (B <= 0 || H <= 0 || Lq <= 0 || Lk <= 0) return cudaErrorInvalidValue;
+  if ((ldq % 8) || (ldk % 8) || (ldv % 8) || (ldo % 2)) return cudaErrorInvalidValue;
+  MhaParams p{q, ldq, k, ldk, v, ldv, out, ldo, key_mask, mask_neg, B, H, Lq, Lk, scale};
+  dim3 grid((Lq + FA_BQ - 1) / FA_BQ, H, B);
+  mha_flash_kernel<<<grid, 128, 0, stream>>>(p);
+  return cudaGetLastError();
+}
+
+}  // namespace fmmt

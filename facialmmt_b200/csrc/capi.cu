@@ -1,34 +1,108 @@
 // extern "C" boundary of libfacialmmt_b200.so (see include/facialmmt_b200.h).
 #include "facialmmt_b200.h"
 
-#include <atomic>
-#include <cstdio>
+#include <new>
 #include <string>
 
-#include "gemm.cuh"
+#include "engine.cuh"
 
 namespace fmmt {
-thread_local std::string g_last_error;
-std::atomic<long long> g_launch_count{0};
+long long launch_count();
 
-int set_error(int code, const std::string& msg) {
-  g_last_error = msg;
-  return code;
-}
-int check_cuda(cudaError_t e, const char* what) {
+
+static int check_cuda(cudaError_t e, const char* what) {
   if (e == cudaSuccess) return FMMT_OK;
+  if (e == cudaErrorInvalidValue) return set_error(FMMT_ERR_INVALID, std::string(what) + ": invalid shape/alignment");
   return set_error(FMMT_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
 }
 }  // namespace fmmt
 
 using namespace fmmt;
 
+struct fmmt_handle {
+  Engine* eng;
+};
+
+static inline cudaStream_t S(void* s) { return static_cast<cudaStream_t>(s); }
+
 extern "C" {
 
 FMMT_API const char* fmmt_last_error(void) { return g_last_error.c_str(); }
 FMMT_API const char* fmmt_version(void) { return "facialmmt_b200 0.1 (sm_100a)"; }
-FMMT_API int64_t fmmt_launch_count(void) { return g_launch_count.load(); }
+FMMT_API int64_t fmmt_launch_count(void) { return launch_count(); }
 
+FMMT_API int fmmt_create(const fmmt_config* cfg, fmmt_handle** out) {
+  if (!cfg || !out) return set_error(FMMT_ERR_INVALID, "fmmt_create: null argument");
+  if (cfg->model < FMMT_MODEL_SWIN_CLS || cfg->model > FMMT_MODEL_UNIMODAL)
+    return set_error(FMMT_ERR_INVALID, "fmmt_create: unknown model kind");
+  fmmt_handle* h = new (std::nothrow) fmmt_handle;
+  if (!h) return set_error(FMMT_ERR_STATE, "out of host memory");
+  h->eng = new (std::nothrow) Engine(*cfg);
+  if (!h->eng) {
+    delete h;
+    return set_error(FMMT_ERR_STATE, "out of host memory");
+  }
+  *out = h;
+  return FMMT_OK;
+}
+
+FMMT_API void fmmt_destroy(fmmt_handle* h) {
+  if (!h) return;
+  delete h->eng;
+  delete h;
+}
+
+FMMT_API int fmmt_load_weight(fmmt_handle* h, const char* ref_key, const float* data, const int64_t* shape, int ndim) {
+  if (!h) return set_error(FMMT_ERR_INVALID, "null handle");
+  return h->eng->load_weight(ref_key, data, shape, ndim);
+}
+
+FMMT_API int fmmt_finalize(fmmt_handle* h) {
+  if (!h) return set_error(FMMT_ERR_INVALID, "null handle");
+  return h->eng->finalize();
+}
+
+FMMT_API int fmmt_swin_forward(fmmt_handle* h, const float* frames, int n_frames, const float* gumbel, float tau,
+                               float* logits, float* probs, float* importance, float* feat, void* stream) {
+  if (!h) return set_error(FMMT_ERR_INVALID, "null handle");
+  return h->eng->swin_forward(frames, n_frames, gumbel, tau, logits, probs, importance, feat, S(stream));
+}
+
+FMMT_API int fmmt_filter_pack(const float* vision, const float* vision_mask, const int32_t* frame_off, int total_frames,
+                              const float* probs, float threshold, int per_utterance, float* out_v, float* out_mask,
+                              int32_t* scratch, int U, int Lv, int D, int labels, void* stream) {
+  if (!vision || !vision_mask || !frame_off || !probs || !out_v || !out_mask)
+    return set_error(FMMT_ERR_INVALID, "fmmt_filter_pack: null pointer");
+  count_launch(per_utterance ? 1 : 2);
+  return check_cuda(launch_filter_pack(vision, vision_mask, frame_off, total_frames, probs, threshold, per_utterance, out_v,
+                                       out_mask, scratch, U, Lv, D, labels, S(stream)),
+                    "fmmt_filter_pack");
+}
+
+FMMT_API int fmmt_multimodal_forward(fmmt_handle* h, const int64_t* ids, const int64_t* mask, const int64_t* sep_mask,
+                                     const float* audio, const float* audio_mask, const float* vision,
+                                     const float* vision_mask, const int64_t* idx_in_dia, int U, int L, float* logits,
+                                     void* stream) {
+  if (!h) return set_error(FMMT_ERR_INVALID, "null handle");
+  return h->eng->multimodal_forward(ids, mask, sep_mask, audio, audio_mask, vision, vision_mask, idx_in_dia, U, L, logits,
+                                    S(stream));
+}
+
+FMMT_API int fmmt_unimodal_forward(fmmt_handle* h, const float* inputs, const float* utt_mask, int U, float* logits,
+                                   void* stream) {
+  if (!h) return set_error(FMMT_ERR_INVALID, "null handle");
+  return h->eng->unimodal_forward(inputs, utt_mask, U, logits, S(stream));
+}
+
+FMMT_API int fmmt_set_capture(fmmt_handle* h, const char* name, float* dst, int64_t count) {
+  if (!h) return set_error(FMMT_ERR_INVALID, "null handle");
+  return h->eng->set_capture(name, dst, count);
+}
+
+FMMT_API double fmmt_flops(fmmt_handle* h, int reset) { return h ? h->eng->flops(reset != 0) : 0.0; }
+FMMT_API int64_t fmmt_device_bytes(fmmt_handle* h) { return h ? h->eng->device_bytes() : 0; }
+
+// ------------------------------------------------------------------------------------------------ operator level
 FMMT_API int fmmt_op_gemm(const void* A_bf16, int lda, const void* W_bf16, int ldw, int M, int N, int K,
                           const float* bias, int act, const float* residual, int ldr, float* out_f32, int ldo32,
                           void* out_bf16, int ldo16, const int* row_map, int map_period, int block_n, void* stream) {
@@ -43,10 +117,42 @@ FMMT_API int fmmt_op_gemm(const void* A_bf16, int lda, const void* W_bf16, int l
   a.out_bf16 = static_cast<__nv_bfloat16*>(out_bf16); a.ldo16 = ldo16;
   a.row_map = row_map; a.map_period = map_period;
   a.block_n = block_n;
-  cudaError_t e = launch_gemm(a, static_cast<cudaStream_t>(stream));
-  if (e == cudaErrorInvalidValue) return set_error(FMMT_ERR_INVALID, "fmmt_op_gemm: invalid shape/alignment");
-  g_launch_count.fetch_add(1);
-  return check_cuda(e, "fmmt_op_gemm");
+  count_launch();
+  return check_cuda(launch_gemm(a, S(stream)), "fmmt_op_gemm");
+}
+
+FMMT_API int fmmt_op_layernorm(const float* in, int ld_in, int M, int nseg, int cseg, const int* map, int map_period,
+                               int src_period, const float* gamma, const float* beta, float eps, float* out_f32,
+                               int ld32, void* out_bf16, int ld16, void* stream) {
+  if (!in || !gamma || !beta || (!out_f32 && !out_bf16)) return set_error(FMMT_ERR_INVALID, "fmmt_op_layernorm: null pointer");
+  LnArgs a;
+  a.in = in; a.ld_in = ld_in; a.M = M; a.nseg = nseg; a.cseg = cseg;
+  a.map = map; a.map_period = map_period; a.src_period = src_period;
+  a.gamma = gamma; a.beta = beta; a.eps = eps;
+  a.out_f32 = out_f32; a.ld32 = ld32;
+  a.out_bf16 = static_cast<__nv_bfloat16*>(out_bf16); a.ld16 = ld16;
+  count_launch();
+  return check_cuda(launch_layernorm(a, S(stream)), "fmmt_op_layernorm");
+}
+
+FMMT_API int fmmt_op_window_attention(const void* qkv_bf16, void* out_bf16, const float* bias, const int8_t* rid,
+                                      int num_windows, int nW, int heads, int C, int N, float scale, void* stream) {
+  if (!qkv_bf16 || !out_bf16 || !bias) return set_error(FMMT_ERR_INVALID, "fmmt_op_window_attention: null pointer");
+  count_launch();
+  return check_cuda(launch_window_attention(static_cast<const __nv_bfloat16*>(qkv_bf16),
+                                            static_cast<__nv_bfloat16*>(out_bf16), bias, rid, num_windows, nW, heads, C,
+                                            N, scale, S(stream)),
+                    "fmmt_op_window_attention");
+}
+
+FMMT_API int fmmt_op_mha(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv, void* out, int ldo,
+                         const float* key_mask, float mask_neg, int B, int H, int Lq, int Lk, float scale, void* stream) {
+  if (!q || !k || !v || !out) return set_error(FMMT_ERR_INVALID, "fmmt_op_mha: null pointer");
+  count_launch();
+  return check_cuda(launch_mha(static_cast<const __nv_bfloat16*>(q), ldq, static_cast<const __nv_bfloat16*>(k), ldk,
+                               static_cast<const __nv_bfloat16*>(v), ldv, static_cast<__nv_bfloat16*>(out), ldo, key_mask,
+                               mask_neg, B, H, Lq, Lk, scale, S(stream)),
+                    "fmmt_op_mha");
 }
 
 }  // extern "C"

@@ -1,0 +1,897 @@
+// Engine implementation: weight packing (reference state_dict -> device layouts) and forward orchestration.
+#include "engine.cuh"
+
+#include <atomic>
+#include <cmath>
+#include <cstring>
+#include <stdexcept>
+
+namespace fmmt {
+
+thread_local std::string g_last_error;
+static std::atomic<long long> g_launches{0};
+int set_error(int code, const std::string& msg) {
+  g_last_error = msg;
+  return code;
+}
+void count_launch(int n) { g_launches.fetch_add(n); }
+long long launch_count() { return g_launches.load(); }
+
+namespace {
+int round_up(int v, int m) { return (v + m - 1) / m * m; }
+struct PackError : std::runtime_error {
+  using std::runtime_error::runtime_error;
+};
+}  // namespace
+
+// =================================================================================================== lifecycle
+Engine::Engine(const fmmt_config& cfg) : cfg_(cfg) {}
+
+Engine::~Engine() {
+  cudaDeviceSynchronize();
+  for (void* p : dev_ptrs_) cudaFree(p);
+  if (ws_) cudaFree(ws_);
+}
+
+int Engine::load_weight(const char* key, const float* data, const int64_t* shape, int ndim) {
+  if (finalized_) return set_error(FMMT_ERR_STATE, "fmmt_load_weight after fmmt_finalize");
+  if (!key || !data || ndim < 0 || ndim > 8) return set_error(FMMT_ERR_INVALID, "fmmt_load_weight: bad arguments");
+  HostTensor t;
+  t.shape.assign(shape, shape + ndim);
+  const int64_t n = t.numel();
+  if (n <= 0) return set_error(FMMT_ERR_INVALID, std::string("fmmt_load_weight: empty tensor ") + key);
+  t.data.assign(data, data + n);
+  host_[key] = std::move(t);
+  return FMMT_OK;
+}
+
+const HostTensor* Engine::find(const std::string& key) {
+  auto it = host_.find(key);
+  return it == host_.end() ? nullptr : &it->second;
+}
+const HostTensor& Engine::need(const std::string& key) {
+  const HostTensor* t = find(key);
+  if (!t) throw PackError("missing weight: " + key);
+  return *t;
+}
+
+template <typename T>
+T* Engine::dev_alloc(size_t n) {
+  void* p = nullptr;
+  const size_t bytes = (n * sizeof(T) + 255) & ~static_cast<size_t>(255);
+  cudaError_t e = cudaMalloc(&p, bytes);
+  if (e != cudaSuccess) throw PackError(std::string("cudaMalloc failed: ") + cudaGetErrorString(e));
+  dev_ptrs_.push_back(p);
+  weight_bytes_ += bytes;
+  return static_cast<T*>(p);
+}
+
+float* Engine::up_f32(const float* src, size_t n) {
+  float* d = dev_alloc<float>(n);
+  cudaError_t e = cudaMemcpy(d, src, n * sizeof(float), cudaMemcpyHostToDevice);
+  if (e != cudaSuccess) throw PackError(std::string("cudaMemcpy failed: ") + cudaGetErrorString(e));
+  return d;
+}
+
+bf16* Engine::up_bf16(const float* src, int rows, int cols, int ld) {
+  std::vector<bf16> tmp(static_cast<size_t>(rows) * ld, __float2bfloat16(0.f));
+  for (int r = 0; r < rows; ++r)
+    for (int c = 0; c < cols; ++c) tmp[static_cast<size_t>(r) * ld + c] = __float2bfloat16(src[static_cast<size_t>(r) * cols + c]);
+  bf16* d = dev_alloc<bf16>(tmp.size());
+  cudaError_t e = cudaMemcpy(d, tmp.data(), tmp.size() * sizeof(bf16), cudaMemcpyHostToDevice);
+  if (e != cudaSuccess) throw PackError(std::string("cudaMemcpy failed: ") + cudaGetErrorString(e));
+  return d;
+}
+
+Lin Engine::make_lin(const float* w, const float* b, int N, int K) {
+  Lin l;
+  l.N = N; l.K = K; l.ld = round_up(K, 8);
+  l.w = up_bf16(w, N, K, l.ld);
+  if (b) l.b = up_f32(b, N);
+  return l;
+}
+
+Lin Engine::lin(const std::string& prefix, bool bias) {
+  const HostTensor& w = need(prefix + "weight");
+  if (w.shape.size() < 2) throw PackError("not a matrix: " + prefix + "weight");
+  const int N = static_cast<int>(w.shape[0]);
+  const int K = static_cast<int>(w.numel() / N);
+  const float* b = nullptr;
+  if (bias) {
+    const HostTensor& bt = need(prefix + "bias");
+    if (bt.numel() != N) throw PackError("bias shape mismatch: " + prefix);
+    b = bt.data.data();
+  }
+  return make_lin(w.data.data(), b, N, K);
+}
+
+Norm Engine::norm(const std::string& prefix) {
+  const HostTensor& g = need(prefix + "weight");
+  const HostTensor& b = need(prefix + "bias");
+  if (g.numel() != b.numel()) throw PackError("norm shape mismatch: " + prefix);
+  Norm n;
+  n.C = static_cast<int>(g.numel());
+  n.g = up_f32(g.data.data(), n.C);
+  n.b = up_f32(b.data.data(), n.C);
+  return n;
+}
+
+static void expect(bool ok, const std::string& what) {
+  if (!ok) throw PackError("shape check failed: " + what);
+}
+
+// --------------------------------------------------------------------------------------------------- Swin packing
+void Engine::pack_swin() {
+  const fmmt_config& c = cfg_;
+  expect(c.patch_size == 4 && c.in_chans == 3, "patch_size 4 / in_chans 3");
+  expect(c.num_stages >= 1 && c.num_stages <= 4, "1..4 stages");
+  expect(c.img_size % (c.patch_size << (c.num_stages - 1)) == 0, "img_size divisible by patch * 2^(stages-1)");
+  swin_.patch = lin("swin.patch_embed.proj.");
+  expect(swin_.patch.N == c.embed_dim && swin_.patch.K == 48, "patch_embed.proj (C,3,4,4)");
+  swin_.patch_ln = norm("swin.patch_embed.norm.");
+  int R = c.img_size / c.patch_size, C = c.embed_dim;
+  for (int li = 0; li < c.num_stages; ++li) {
+    SwinStageW sw;
+    sw.R = R; sw.C = C; sw.heads = c.num_heads[li];
+    expect(C == sw.heads * 32, "Swin head_dim must be 32 (C / heads)");
+    // Swin_Transformer.py:192-195: if the resolution does not exceed the window, one window, no shift
+    const bool shiftable = R > c.window_size;
+    sw.ws = shiftable ? c.window_size : R;
+    expect(R % sw.ws == 0, "resolution divisible by window");
+    sw.N = sw.ws * sw.ws;
+    expect(sw.N <= 49, "window tokens <= 49");
+    const int nw = R / sw.ws;
+    sw.nW = nw * nw;
+    const int T = R * R;
+    const int s = c.window_size / 2;
+    for (int v = 0; v < 2; ++v) {
+      const int shift = v == 0 ? 0 : (shiftable ? s : 0);
+      std::vector<int> map(T);
+      // window-order row (wy,wx,ty,tx) reads token ((wy*ws+ty+shift)%R, (wx*ws+tx+shift)%R): torch.roll(-shift) then
+      // window_partition (Swin_Transformer.py:244,43-44); the same map scatters back (window_reverse + roll(+shift)).
+      int r = 0;
+      for (int wy = 0; wy < nw; ++wy)
+        for (int wx = 0; wx < nw; ++wx)
+          for (int ty = 0; ty < sw.ws; ++ty)
+            for (int tx = 0; tx < sw.ws; ++tx) {
+              const int hh = (wy * sw.ws + ty + shift) % R, ww = (wx * sw.ws + tx + shift) % R;
+              map[r++] = hh * R + ww;
+            }
+      int* d = dev_alloc<int>(T);
+      cudaMemcpy(d, map.data(), T * sizeof(int), cudaMemcpyHostToDevice);
+      sw.win_map[v] = d;
+    }
+    if (shiftable) {
+      // region ids in shifted coordinates (Swin_Transformer.py:208-229): mask[i][j] = rid_i != rid_j ? -100 : 0
+      std::vector<int8_t> rid(static_cast<size_t>(sw.nW) * sw.N);
+      auto region = [&](int p) { return p < R - sw.ws ? 0 : (p < R - s ? 1 : 2); };
+      int r = 0;
+      for (int wy = 0; wy < nw; ++wy)
+        for (int wx = 0; wx < nw; ++wx)
+          for (int ty = 0; ty < sw.ws; ++ty)
+            for (int tx = 0; tx < sw.ws; ++tx)
+              rid[r++] = static_cast<int8_t>(3 * region(wy * sw.ws + ty) + region(wx * sw.ws + tx));
+      sw.rid = dev_alloc<int8_t>(rid.size());
+      cudaMemcpy(sw.rid, rid.data(), rid.size(), cudaMemcpyHostToDevice);
+    }
+    for (int bi = 0; bi < c.depths[li]; ++bi) {
+      const std::string p = "swin.layers." + std::to_string(li) + ".blocks." + std::to_string(bi) + ".";
+      SwinBlockW bw;
+      bw.shift = (bi % 2 == 1 && shiftable) ? s : 0;
+      bw.ln1 = norm(p + "norm1.");
+      bw.ln2 = norm(p + "norm2.");
+      bw.qkv = lin(p + "attn.qkv.");
+      bw.proj = lin(p + "attn.proj.");
+      bw.fc1 = lin(p + "mlp.fc1.");
+      bw.fc2 = lin(p + "mlp.fc2.");
+      expect(bw.qkv.N == 3 * C && bw.qkv.K == C && bw.proj.N == C && bw.fc1.K == C && bw.fc2.N == C &&
+                 bw.fc2.K == bw.fc1.N && bw.ln1.C == C,
+             p + " dims");
+      const HostTensor& tab = need(p + "attn.relative_position_bias_table");
+      const int span = 2 * sw.ws - 1;
+      expect(tab.numel() == static_cast<int64_t>(span) * span * sw.heads, p + "relative_position_bias_table");
+      std::vector<float> be(static_cast<size_t>(sw.heads) * sw.N * sw.N);
+      for (int i = 0; i < sw.N; ++i)
+        for (int j = 0; j < sw.N; ++j) {
+          const int yi = i / sw.ws, xi = i % sw.ws, yj = j / sw.ws, xj = j % sw.ws;
+          const int idx = (yi - yj + sw.ws - 1) * span + (xi - xj + sw.ws - 1);
+          for (int h = 0; h < sw.heads; ++h)
+            be[(static_cast<size_t>(h) * sw.N + i) * sw.N + j] = tab.data[static_cast<size_t>(idx) * sw.heads + h];
+        }
+      bw.bias_exp = up_f32(be.data(), be.size());
+      sw.blocks.push_back(bw);
+    }
+    if (li < c.num_stages - 1) {
+      const std::string p = "swin.layers." + std::to_string(li) + ".downsample.";
+      sw.has_merge = true;
+      sw.merge_ln = norm(p + "norm.");
+      sw.merge = lin(p + "reduction.", false);
+      expect(sw.merge.K == 4 * C && sw.merge.N == 2 * C && sw.merge_ln.C == 4 * C, p + " dims");
+      const int R2 = R / 2;
+      std::vector<int> mm(static_cast<size_t>(R2) * R2 * 4);
+      for (int y = 0; y < R2; ++y)
+        for (int x = 0; x < R2; ++x) {
+          int* q = &mm[(static_cast<size_t>(y) * R2 + x) * 4];
+          q[0] = (2 * y) * R + 2 * x;          // x0 = x[0::2, 0::2]   (Swin_Transformer.py:318-322)
+          q[1] = (2 * y + 1) * R + 2 * x;      // x1 = x[1::2, 0::2]
+          q[2] = (2 * y) * R + 2 * x + 1;      // x2 = x[0::2, 1::2]
+          q[3] = (2 * y + 1) * R + 2 * x + 1;  // x3 = x[1::2, 1::2]
+        }
+      sw.merge_map = dev_alloc<int>(mm.size());
+      cudaMemcpy(sw.merge_map, mm.data(), mm.size() * sizeof(int), cudaMemcpyHostToDevice);
+    }
+    swin_.stages.push_back(sw);
+    if (li < c.num_stages - 1) { R /= 2; C *= 2; }
+  }
+  swin_.head_ln = norm("swin.output_layer.0.");
+  expect(swin_.head_ln.C == C, "output_layer.0");
+  {
+    // Linear(R*R*C, feat) followed by BatchNorm1d(eval) (Swin_Transformer.py:493-494): fold BN into the Linear.
+    const HostTensor& w = need("swin.output_layer.2.weight");
+    const HostTensor& b = need("swin.output_layer.2.bias");
+    const HostTensor& g = need("swin.output_layer.3.weight");
+    const HostTensor& be = need("swin.output_layer.3.bias");
+    const HostTensor& mu = need("swin.output_layer.3.running_mean");
+    const HostTensor& var = need("swin.output_layer.3.running_var");
+    const int N = c.feat_dim, K = R * R * C;
+    expect(w.numel() == static_cast<int64_t>(N) * K && b.numel() == N && g.numel() == N && mu.numel() == N, "output_layer");
+    std::vector<float> wf(w.data), bf(N);
+    for (int n = 0; n < N; ++n) {
+      const float sc = g.data[n] / std::sqrt(var.data[n] + 1e-5f);
+      for (int k = 0; k < K; ++k) wf[static_cast<size_t>(n) * K + k] *= sc;
+      bf[n] = (b.data[n] - mu.data[n]) * sc + be.data[n];
+    }
+    swin_.head = make_lin(wf.data(), bf.data(), N, K);
+  }
+  {
+    const HostTensor& w1 = need("linear.weight");
+    const HostTensor& b1 = need("linear.bias");
+    const HostTensor& w2 = need("classifier.weight");
+    const HostTensor& b2 = need("classifier.bias");
+    const int Fd = c.feat_dim, Hh = c.head_hidden, Lb = c.num_labels;
+    expect(w1.numel() == static_cast<int64_t>(Hh) * Fd && w2.numel() == static_cast<int64_t>(Lb) * Hh, "swin head dims");
+    std::vector<float> w1t(static_cast<size_t>(Fd) * Hh);
+    for (int j = 0; j < Hh; ++j)
+      for (int k = 0; k < Fd; ++k) w1t[static_cast<size_t>(k) * Hh + j] = w1.data[static_cast<size_t>(j) * Fd + k];
+    swin_.w1t = up_f32(w1t.data(), w1t.size());
+    swin_.b1 = up_f32(b1.data.data(), Hh);
+    swin_.w2 = up_f32(w2.data.data(), w2.data.size());
+    swin_.b2 = up_f32(b2.data.data(), Lb);
+  }
+}
+
+// --------------------------------------------------------------------------------------------------- fusion packing
+EncLayerW Engine::enc_layer(const std::string& qkv_prefix, const std::string& o_prefix, const std::string& ln1_prefix,
+                            const std::string& fc1_prefix, const std::string& fc2_prefix, const std::string& ln2_prefix,
+                            int H) {
+  EncLayerW l;
+  // separate query / key / value Linear layers -> one [3H, H] GEMM
+  std::vector<float> w(static_cast<size_t>(3) * H * H), b(static_cast<size_t>(3) * H);
+  const char* names[3] = {"query.", "key.", "value."};
+  for (int i = 0; i < 3; ++i) {
+    const HostTensor& wi = need(qkv_prefix + names[i] + "weight");
+    const HostTensor& bi = need(qkv_prefix + names[i] + "bias");
+    expect(wi.numel() == static_cast<int64_t>(H) * H && bi.numel() == H, qkv_prefix + names[i]);
+    std::memcpy(&w[static_cast<size_t>(i) * H * H], wi.data.data(), sizeof(float) * H * H);
+    std::memcpy(&b[static_cast<size_t>(i) * H], bi.data.data(), sizeof(float) * H);
+  }
+  l.qkv = make_lin(w.data(), b.data(), 3 * H, H);
+  l.o = lin(o_prefix);
+  l.ln1 = norm(ln1_prefix);
+  l.fc1 = lin(fc1_prefix);
+  l.fc2 = lin(fc2_prefix);
+  l.ln2 = norm(ln2_prefix);
+  expect(l.o.N == H && l.o.K == H && l.fc1.K == H && l.fc2.N == H && l.fc2.K == l.fc1.N && l.ln1.C == H && l.ln2.C == H,
+         o_prefix + " dims");
+  return l;
+}
+
+void Engine::pack_text() {
+  const fmmt_config& c = cfg_;
+  const std::string p = c.text_kind == FMMT_TEXT_ROBERTA ? "roberta." : "bert.";
+  const int D = c.text_hidden;
+  expect(D == c.text_heads * 64, "text head_dim must be 64");
+  const HostTensor& we = need(p + "embeddings.word_embeddings.weight");
+  const HostTensor& pe = need(p + "embeddings.position_embeddings.weight");
+  const HostTensor& te = need(p + "embeddings.token_type_embeddings.weight");
+  expect(we.numel() == static_cast<int64_t>(c.vocab_size) * D && pe.numel() == static_cast<int64_t>(c.max_pos) * D &&
+             te.numel() >= D,
+         "text embeddings");
+  text_.word = up_f32(we.data.data(), we.data.size());
+  text_.pos = up_f32(pe.data.data(), pe.data.size());
+  text_.type0 = up_f32(te.data.data(), D);
+  text_.emb_ln = norm(p + "embeddings.LayerNorm.");
+  for (int i = 0; i < c.text_layers; ++i) {
+    const std::string q = p + "encoder.layer." + std::to_string(i) + ".";
+    text_.layers.push_back(enc_layer(q + "attention.self.", q + "attention.output.dense.", q + "attention.output.LayerNorm.",
+                                     q + "intermediate.dense.", q + "output.dense.", q + "output.LayerNorm.", D));
+    expect(text_.layers.back().fc1.N == c.text_ffn, q + " ffn");
+  }
+  text_.out = lin("text_linear.");
+  expect(text_.out.N == c.hidden && text_.out.K == D, "text_linear");
+}
+
+void Engine::pack_meld(MeldEncW& m, const std::string& lin_prefix, const std::string& enc_prefix, int layers, int in_dim,
+                       int max_len) {
+  const int H = cfg_.hidden;
+  m.in = lin(lin_prefix);
+  expect(m.in.N == H && m.in.K == in_dim, lin_prefix + " dims");
+  const HostTensor& pe = need(enc_prefix + "position_embeddings.weight");
+  expect(pe.numel() == static_cast<int64_t>(max_len) * H, enc_prefix + "position_embeddings");
+  m.pos = up_f32(pe.data.data(), pe.data.size());
+  m.max_len = max_len;
+  for (int i = 0; i < layers; ++i) {
+    const std::string q = enc_prefix + "layer." + std::to_string(i) + ".";
+    const std::string a = q + "transformer_self_attention.";
+    m.layers.push_back(enc_layer(a + "selfatt.", a + "dense_norm.dense.", a + "dense_norm.LayerNorm.",
+                                 q + "intermediate.dense.", q + "output.dense.", q + "output.LayerNorm.", H));
+    expect(m.layers.back().fc1.N == cfg_.ffn, q + " ffn");
+  }
+}
+
+void Engine::pack_cmt(CmtW& cw, const std::string& prefix, int layers, int heads) {
+  const int H = cfg_.hidden;
+  expect(H == heads * 64, prefix + " head_dim must be 64");
+  cw.heads = heads;
+  for (int i = 0; i < layers; ++i) {
+    const std::string p = prefix + "layers." + std::to_string(i) + ".";
+    CmtLayerW l;
+    const HostTensor& w = need(p + "self_attn.in_proj_weight");
+    const HostTensor& b = need(p + "self_attn.in_proj_bias");
+    expect(w.numel() == static_cast<int64_t>(3) * H * H && b.numel() == 3 * H, p + "in_proj");
+    // packed (3H,H): rows [0,H) = Q, [H,2H) = K, [2H,3H) = V (multihead_attention.py:137-158)
+    l.q = make_lin(w.data.data(), b.data.data(), H, H);
+    l.kv = make_lin(w.data.data() + static_cast<size_t>(H) * H, b.data.data() + H, 2 * H, H);
+    l.o = lin(p + "self_attn.out_proj.");
+    l.fc1 = lin(p + "fc1.");
+    l.fc2 = lin(p + "fc2.");
+    l.ln0 = norm(p + "layer_norms.0.");
+    l.ln1 = norm(p + "layer_norms.1.");
+    expect(l.fc1.K == H && l.fc2.N == H && l.fc2.K == l.fc1.N, p + " dims");
+    cw.layers.push_back(l);
+  }
+  cw.final_ln = norm(prefix + "layer_norm.");
+}
+
+void Engine::pack_pool(const std::string& prefix, const std::string& cls_prefix) {
+  const int H = cfg_.hidden;
+  const HostTensor& qv = need(prefix + "query_vector");
+  const HostTensor& Pw = need(prefix + "P.weight");
+  const HostTensor& Pb = need(prefix + "P.bias");
+  const HostTensor& Qw = need(prefix + "Q.weight");
+  const HostTensor& Qb = need(prefix + "Q.bias");
+  const HostTensor& vw = need(prefix + "value.weight");
+  const HostTensor& vb = need(prefix + "value.bias");
+  expect(qv.numel() == H && Pw.numel() == static_cast<int64_t>(H) * H && Qw.numel() == static_cast<int64_t>(H) * H &&
+             vw.numel() == H,
+         prefix + " dims");
+  // torch.add(P(inputs), Q(query_vector)) (modules/Transformer.py:34): the Q term is input independent
+  std::vector<float> pb(H);
+  for (int n = 0; n < H; ++n) {
+    double acc = Qb.data[n];
+    for (int k = 0; k < H; ++k) acc += static_cast<double>(Qw.data[static_cast<size_t>(n) * H + k]) * qv.data[k];
+    pb[n] = Pb.data[n] + static_cast<float>(acc);
+  }
+  pool_.P = make_lin(Pw.data.data(), pb.data(), H, H);
+  pool_.wv = up_f32(vw.data.data(), H);
+  pool_.bv = vb.data[0];
+  const HostTensor& cw = need(cls_prefix + "weight");
+  const HostTensor& cb = need(cls_prefix + "bias");
+  expect(cw.numel() == static_cast<int64_t>(cfg_.num_labels) * H && cb.numel() == cfg_.num_labels, cls_prefix);
+  pool_.wc = up_f32(cw.data.data(), cw.data.size());
+  pool_.bc = up_f32(cb.data.data(), cb.data.size());
+}
+
+void Engine::build_sinusoid(int max_len) {
+  // SinusoidalPositionalEmbedding.get_embedding (modules/position_embedding.py:45-60), padding_idx 0 -> zero row.
+  const int H = cfg_.hidden, half = H / 2;
+  std::vector<float> tab(static_cast<size_t>(max_len + 1) * H, 0.f);
+  const float e = static_cast<float>(-(std::log(10000.0) / (half - 1)));
+  for (int p = 1; p <= max_len; ++p)
+    for (int j = 0; j < half; ++j) {
+      const float fj = expf(static_cast<float>(j) * e);
+      const float ang = static_cast<float>(p) * fj;
+      tab[static_cast<size_t>(p) * H + j] = sinf(ang);
+      tab[static_cast<size_t>(p) * H + half + j] = cosf(ang);
+    }
+  sinusoid_ = up_f32(tab.data(), tab.size());
+  sinusoid_len_ = max_len;
+}
+
+int Engine::finalize() {
+  if (finalized_) return FMMT_OK;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+    return set_error(FMMT_ERR_CUDA, "no CUDA device: facialmmt_b200 has no CPU fallback");
+  try {
+    const fmmt_config& c = cfg_;
+    if (c.model == FMMT_MODEL_SWIN_CLS) {
+      pack_swin();
+    } else if (c.model == FMMT_MODEL_MULTIMODAL) {
+      expect(c.hidden == c.heads * 64, "fusion head_dim must be 64");
+      pack_text();
+      pack_meld(audio_, "audio_linear.", "audio_utt_transformer.", c.audio_layers, c.audio_dim, c.audio_len);
+      pack_meld(vision_, "vision_linear.", "vision_utt_transformer.", c.vision_layers, c.vision_dim + c.num_labels,
+                c.vision_len);
+      pack_cmt(cmt_ta_, "CrossModalTrans_TA.", c.cmt_layers_ta, c.cmt_heads_ta);
+      pack_cmt(cmt_tav_, "CrossModalTrans_TA_V.", c.cmt_layers_tav, c.cmt_heads_tav);
+      pack_pool("attention.", "classifier.");
+      build_sinusoid(c.text_len + c.audio_len + c.vision_len);
+    } else if (c.model == FMMT_MODEL_UNIMODAL) {
+      expect(c.hidden == c.heads * 64, "fusion head_dim must be 64");
+      pack_meld(vision_, "modality_linear.", "utt_transformer.", c.vision_layers, c.vision_dim, c.vision_len);
+      pack_pool("attention.", "classifier.");
+    } else {
+      return set_error(FMMT_ERR_INVALID, "unknown model kind");
+    }
+  } catch (const PackError& e) {
+    return set_error(FMMT_ERR_STATE, std::string("fmmt_finalize: ") + e.what());
+  }
+  cudaError_t e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) return set_error(FMMT_ERR_CUDA, std::string("fmmt_finalize: ") + cudaGetErrorString(e));
+  host_.clear();
+  finalized_ = true;
+  return FMMT_OK;
+}
+
+int Engine::set_capture(const char* name, float* dst, int64_t count) {
+  if (!name) {
+    caps_.clear();
+    return FMMT_OK;
+  }
+  if (!dst || count <= 0) caps_.erase(name);
+  else caps_[name] = Cap{dst, count};
+  return FMMT_OK;
+}
+
+// =================================================================================================== op wrappers
+void Engine::ck(cudaError_t e, const char* what) {
+  if (e != cudaSuccess && first_err_ == cudaSuccess) {
+    first_err_ = e;
+    err_ = std::string(what) + ": " + cudaGetErrorString(e);
+  }
+}
+
+void Engine::gemm(GemmArgs a) {
+  if (arena_.dry() || first_err_ != cudaSuccess) return;
+  flops_ += gemm_flops(a);
+  count_launch();
+  ck(launch_gemm(a, st_), "gemm");
+}
+
+void Engine::gemm_lin(const bf16* A, int lda, int M, const Lin& l, GemmArgs ep) {
+  ep.A = A; ep.lda = lda; ep.M = M;
+  ep.W = l.w; ep.ldw = l.ld; ep.N = l.N; ep.K = l.K;
+  ep.bias = l.b;
+  gemm(ep);
+}
+
+void Engine::ln(LnArgs a) {
+  if (arena_.dry() || first_err_ != cudaSuccess) return;
+  count_launch();
+  ck(launch_layernorm(a, st_), "layernorm");
+}
+
+void Engine::capture(const std::string& name, const float* src, size_t count, size_t dst_off) {
+  if (arena_.dry() || first_err_ != cudaSuccess || caps_.empty()) return;
+  auto it = caps_.find(name);
+  if (it == caps_.end()) return;
+  if (dst_off + count > static_cast<size_t>(it->second.count)) {
+    if (dst_off >= static_cast<size_t>(it->second.count)) return;
+    count = it->second.count - dst_off;
+  }
+  ck(cudaMemcpyAsync(it->second.dst + dst_off, src, count * sizeof(float), cudaMemcpyDeviceToDevice, st_), "capture");
+}
+
+#define OP(call, what)                                         \
+  do {                                                         \
+    if (!arena_.dry() && first_err_ == cudaSuccess) {          \
+      count_launch();                                          \
+      ck((call), what);                                        \
+    }                                                          \
+  } while (0)
+
+template <typename Fn>
+int Engine::run(Fn&& body, cudaStream_t st) {
+  if (!finalized_) return set_error(FMMT_ERR_STATE, "handle is not finalized (call fmmt_finalize)");
+  st_ = st;
+  first_err_ = cudaSuccess;
+  err_.clear();
+  arena_.begin(true, nullptr, 0);
+  body();
+  const size_t need_bytes = arena_.peak() + 256;
+  if (need_bytes > ws_cap_) {
+    cudaError_t e = cudaDeviceSynchronize();  // earlier forwards may still be using the old workspace
+    if (e != cudaSuccess) return set_error(FMMT_ERR_CUDA, std::string("workspace sync: ") + cudaGetErrorString(e));
+    if (ws_) cudaFree(ws_);
+    ws_ = nullptr;
+    ws_cap_ = 0;
+    void* p = nullptr;
+    e = cudaMalloc(&p, need_bytes);
+    if (e != cudaSuccess) return set_error(FMMT_ERR_CUDA, std::string("workspace cudaMalloc: ") + cudaGetErrorString(e));
+    ws_ = static_cast<char*>(p);
+    ws_cap_ = need_bytes;
+  }
+  arena_.begin(false, ws_, ws_cap_);
+  body();
+  if (first_err_ != cudaSuccess) return set_error(first_err_ == cudaErrorInvalidValue ? FMMT_ERR_INVALID : FMMT_ERR_CUDA, err_);
+  return FMMT_OK;
+}
+
+// =================================================================================================== Swin forward
+void Engine::swin_block(const SwinStageW& sw, const SwinBlockW& bw, float* x, int nf, bf16* h, bf16* qkv, bf16* a,
+                        bf16* hid) {
+  const int T = sw.R * sw.R, C = sw.C, M = nf * T;
+  const int* map = sw.win_map[bw.shift ? 1 : 0];
+  LnArgs l1;
+  l1.in = x; l1.ld_in = C; l1.M = M; l1.nseg = 1; l1.cseg = C;
+  l1.map = map; l1.map_period = T; l1.src_period = T;
+  l1.gamma = bw.ln1.g; l1.beta = bw.ln1.b; l1.eps = 1e-5f;
+  l1.out_bf16 = h; l1.ld16 = C;
+  ln(l1);                                                           // norm1 + roll + window_partition
+  GemmArgs g1;
+  g1.out_bf16 = qkv; g1.ldo16 = 3 * C;
+  gemm_lin(h, C, M, bw.qkv, g1);                                    // qkv Linear
+  if (!arena_.dry() && first_err_ == cudaSuccess) {
+    count_launch();
+    flops_ += 4.0 * M * sw.N * C;
+    ck(launch_window_attention(qkv, a, bw.bias_exp, bw.shift ? sw.rid : nullptr, nf * sw.nW, sw.nW, sw.heads, C, sw.N,
+                               1.0f / std::sqrt(32.0f), st_),
+       "window_attention");
+  }
+  GemmArgs g2;
+  g2.residual = x; g2.ldr = C; g2.out_f32 = x; g2.ldo32 = C;
+  g2.row_map = map; g2.map_period = T;
+  gemm_lin(a, C, M, bw.proj, g2);                                   // proj + window_reverse + roll back + shortcut
+  LnArgs l2;
+  l2.in = x; l2.ld_in = C; l2.M = M; l2.cseg = C;
+  l2.gamma = bw.ln2.g; l2.beta = bw.ln2.b; l2.eps = 1e-5f;
+  l2.out_bf16 = h; l2.ld16 = C;
+  ln(l2);                                                           // norm2
+  GemmArgs g3;
+  g3.act = ACT_GELU; g3.out_bf16 = hid; g3.ldo16 = bw.fc1.N;
+  gemm_lin(h, C, M, bw.fc1, g3);                                    // fc1 + GELU
+  GemmArgs g4;
+  g4.residual = x; g4.ldr = C; g4.out_f32 = x; g4.ldo32 = C;
+  gemm_lin(hid, bw.fc1.N, M, bw.fc2, g4);                           // fc2 + residual
+}
+
+static int swin_split(const fmmt_config& c) { return c.num_stages >= 3 ? 2 : (c.num_stages - 1); }
+
+void Engine::swin_early(const float* frames, int f0, int nf, float* x_out) {
+  const fmmt_config& c = cfg_;
+  const int split = swin_split(c);
+  const SwinStageW& s0 = swin_.stages[0];
+  const int T0 = s0.R * s0.R, C0 = s0.C;
+  int M = nf * T0;
+  bf16* col = arena_.alloc<bf16>(static_cast<size_t>(M) * 48);
+  float* x = (split == 0) ? x_out : arena_.alloc<float>(static_cast<size_t>(M) * C0);
+  bf16* h = arena_.alloc<bf16>(static_cast<size_t>(M) * C0);
+  bf16* qkv = arena_.alloc<bf16>(static_cast<size_t>(M) * 3 * C0);
+  bf16* a = arena_.alloc<bf16>(static_cast<size_t>(M) * C0);
+  bf16* hid = arena_.alloc<bf16>(static_cast<size_t>(M) * c.mlp_ratio * C0);
+  const size_t frame_elems = static_cast<size_t>(3) * c.img_size * c.img_size;
+  OP(launch_patch_im2col(frames + static_cast<size_t>(f0) * frame_elems, col, nf, c.img_size, c.img_size, st_), "im2col");
+  GemmArgs g;
+  g.out_f32 = x; g.ldo32 = C0;
+  gemm_lin(col, 48, M, swin_.patch, g);                              // Conv2d(3,96,k4,s4) as GEMM (K = 48)
+  LnArgs l;
+  l.in = x; l.ld_in = C0; l.M = M; l.cseg = C0;
+  l.gamma = swin_.patch_ln.g; l.beta = swin_.patch_ln.b; l.eps = 1e-5f;
+  l.out_f32 = x; l.ld32 = C0;
+  ln(l);
+  capture("swin.patch_embed", x, static_cast<size_t>(M) * C0, static_cast<size_t>(f0) * T0 * C0);
+  for (int li = 0; li < split; ++li) {
+    const SwinStageW& sw = swin_.stages[li];
+    const int T = sw.R * sw.R;
+    for (size_t bi = 0; bi < sw.blocks.size(); ++bi) {
+      swin_block(sw, sw.blocks[bi], x, nf, h, qkv, a, hid);
+      capture("swin.layer" + std::to_string(li) + ".block" + std::to_string(bi), x, static_cast<size_t>(nf) * T * sw.C,
+              static_cast<size_t>(f0) * T * sw.C);
+    }
+    LnArgs lm;                                                       // PatchMerging: gather 2x2 -> LN(4C) -> Linear
+    lm.in = x; lm.ld_in = sw.C; lm.M = nf * T / 4; lm.nseg = 4; lm.cseg = sw.C;
+    lm.map = sw.merge_map; lm.map_period = T / 4; lm.src_period = T;
+    lm.gamma = sw.merge_ln.g; lm.beta = sw.merge_ln.b; lm.eps = 1e-5f;
+    lm.out_bf16 = h; lm.ld16 = 4 * sw.C;
+    ln(lm);
+    GemmArgs gm;
+    float* dst = (li == split - 1) ? x_out : x;
+    gm.out_f32 = dst; gm.ldo32 = 2 * sw.C;
+    gemm_lin(h, 4 * sw.C, nf * T / 4, sw.merge, gm);
+  }
+}
+
+void Engine::swin_late(float* x, int f0, int nf, bf16* feat_ln) {
+  const fmmt_config& c = cfg_;
+  const int split = swin_split(c);
+  const SwinStageW& s0 = swin_.stages[split];
+  const size_t M0 = static_cast<size_t>(nf) * s0.R * s0.R;
+  bf16* h = arena_.alloc<bf16>(M0 * s0.C);
+  bf16* qkv = arena_.alloc<bf16>(M0 * 3 * s0.C);
+  bf16* a = arena_.alloc<bf16>(M0 * s0.C);
+  bf16* hid = arena_.alloc<bf16>(M0 * c.mlp_ratio * s0.C);
+  for (int li = split; li < c.num_stages; ++li) {
+    const SwinStageW& sw = swin_.stages[li];
+    const int T = sw.R * sw.R;
+    for (size_t bi = 0; bi < sw.blocks.size(); ++bi) {
+      swin_block(sw, sw.blocks[bi], x, nf, h, qkv, a, hid);
+      capture("swin.layer" + std::to_string(li) + ".block" + std::to_string(bi), x, static_cast<size_t>(nf) * T * sw.C,
+              static_cast<size_t>(f0) * T * sw.C);
+    }
+    if (sw.has_merge) {
+      LnArgs lm;
+      lm.in = x; lm.ld_in = sw.C; lm.M = nf * T / 4; lm.nseg = 4; lm.cseg = sw.C;
+      lm.map = sw.merge_map; lm.map_period = T / 4; lm.src_period = T;
+      lm.gamma = sw.merge_ln.g; lm.beta = sw.merge_ln.b; lm.eps = 1e-5f;
+      lm.out_bf16 = h; lm.ld16 = 4 * sw.C;
+      ln(lm);
+      GemmArgs gm;
+      gm.out_f32 = x; gm.ldo32 = 2 * sw.C;
+      gemm_lin(h, 4 * sw.C, nf * T / 4, sw.merge, gm);
+    }
+  }
+  const SwinStageW& sl = swin_.stages.back();
+  const int Tl = sl.R * sl.R;
+  LnArgs lf;                                                         // output_layer[0]: LayerNorm, token-major flatten
+  lf.in = x; lf.ld_in = sl.C; lf.M = nf * Tl; lf.cseg = sl.C;
+  lf.gamma = swin_.head_ln.g; lf.beta = swin_.head_ln.b; lf.eps = 1e-5f;
+  lf.out_bf16 = feat_ln + static_cast<size_t>(f0) * Tl * sl.C; lf.ld16 = sl.C;
+  ln(lf);
+}
+
+void Engine::swin_body(const float* frames, int F, const float* gumbel, float tau, float* logits, float* probs,
+                       float* importance, float* feat) {
+  const fmmt_config& c = cfg_;
+  const int split = swin_split(c);
+  const SwinStageW& sl = swin_.stages.back();
+  const size_t FL = static_cast<size_t>(sl.R) * sl.R * sl.C;
+  bf16* feat_ln = arena_.alloc<bf16>(static_cast<size_t>(F) * FL);
+  float* feat512 = arena_.alloc<float>(static_cast<size_t>(F) * c.feat_dim);
+  const int big = c.swin_chunk_late > 0 ? c.swin_chunk_late : 64;
+  const int small = c.swin_chunk > 0 ? c.swin_chunk : 16;
+  const SwinStageW& ss = swin_.stages[split];
+  const size_t per_frame_split = static_cast<size_t>(ss.R) * ss.R * ss.C;
+  for (int f0 = 0; f0 < F; f0 += big) {
+    const int nb = std::min(big, F - f0);
+    const size_t mark = arena_.mark();
+    float* x2 = arena_.alloc<float>(static_cast<size_t>(nb) * per_frame_split);
+    for (int g0 = 0; g0 < nb; g0 += small) {
+      const int ns = std::min(small, nb - g0);
+      const size_t m2 = arena_.mark();
+      swin_early(frames, f0 + g0, ns, x2 + static_cast<size_t>(g0) * per_frame_split);
+      arena_.release(m2);
+    }
+    swin_late(x2, f0, nb, feat_ln);
+    arena_.release(mark);
+  }
+  GemmArgs g;                                                        // Linear(49*768, 512) with BatchNorm folded in
+  g.out_f32 = feat512; g.ldo32 = c.feat_dim;
+  gemm_lin(feat_ln, static_cast<int>(FL), F, swin_.head, g);
+  capture("swin.feat", feat512, static_cast<size_t>(F) * c.feat_dim);
+  if (feat != nullptr && !arena_.dry() && first_err_ == cudaSuccess)
+    ck(cudaMemcpyAsync(feat, feat512, static_cast<size_t>(F) * c.feat_dim * sizeof(float), cudaMemcpyDeviceToDevice, st_),
+       "feat copy");
+  OP(launch_swin_tail(feat512, c.feat_dim, swin_.w1t, swin_.b1, c.head_hidden, swin_.w2, swin_.b2, c.num_labels, gumbel,
+                      tau, logits, probs, importance, F, st_),
+     "swin_tail");
+}
+
+int Engine::swin_forward(const float* frames, int F, const float* gumbel, float tau, float* logits, float* probs,
+                         float* importance, float* feat, cudaStream_t st) {
+  if (cfg_.model != FMMT_MODEL_SWIN_CLS) return set_error(FMMT_ERR_STATE, "handle is not a Swin-cls model");
+  if (!frames || F <= 0) return set_error(FMMT_ERR_INVALID, "fmmt_swin_forward: frames/n_frames");
+  if (tau == 0.f) return set_error(FMMT_ERR_INVALID, "fmmt_swin_forward: tau must be non-zero");
+  return run([&] { swin_body(frames, F, gumbel, tau, logits, probs, importance, feat); }, st);
+}
+
+// =================================================================================================== fusion forward
+void Engine::enc_layers(const std::vector<EncLayerW>& layers, float* x32, bf16* x16, int U, int L, int H, int heads,
+                        int ffn, const float* mask01, float mask_neg, float eps) {
+  const int M = U * L;
+  bf16* qkv = arena_.alloc<bf16>(static_cast<size_t>(M) * 3 * H);
+  bf16* ctx = arena_.alloc<bf16>(static_cast<size_t>(M) * H);
+  bf16* hid = arena_.alloc<bf16>(static_cast<size_t>(M) * ffn);
+  for (const EncLayerW& l : layers) {
+    GemmArgs g1;
+    g1.out_bf16 = qkv; g1.ldo16 = 3 * H;
+    gemm_lin(x16, H, M, l.qkv, g1);
+    if (!arena_.dry() && first_err_ == cudaSuccess) {
+      count_launch();
+      flops_ += 4.0 * U * static_cast<double>(L) * L * H;
+      ck(launch_mha(qkv, 3 * H, qkv + H, 3 * H, qkv + 2 * H, 3 * H, ctx, H, mask01, mask_neg, U, heads, L, L, 0.125f, st_),
+         "mha");
+    }
+    GemmArgs g2;
+    g2.residual = x32; g2.ldr = H; g2.out_f32 = x32; g2.ldo32 = H;
+    gemm_lin(ctx, H, M, l.o, g2);
+    LnArgs n1;
+    n1.in = x32; n1.ld_in = H; n1.M = M; n1.cseg = H;
+    n1.gamma = l.ln1.g; n1.beta = l.ln1.b; n1.eps = eps;
+    n1.out_f32 = x32; n1.ld32 = H; n1.out_bf16 = x16; n1.ld16 = H;
+    ln(n1);
+    GemmArgs g3;
+    g3.act = ACT_GELU; g3.out_bf16 = hid; g3.ldo16 = ffn;
+    gemm_lin(x16, H, M, l.fc1, g3);
+    GemmArgs g4;
+    g4.residual = x32; g4.ldr = H; g4.out_f32 = x32; g4.ldo32 = H;
+    gemm_lin(hid, ffn, M, l.fc2, g4);
+    LnArgs n2 = n1;
+    n2.gamma = l.ln2.g; n2.beta = l.ln2.b;
+    ln(n2);
+  }
+}
+
+void Engine::meld_encoder(const MeldEncW& m, const float* in, int in_dim, int U, int L, const float* mask01, float* x32,
+                          bf16* x16) {
+  const int H = cfg_.hidden, M = U * L;
+  const int ldp = round_up(in_dim, 8);
+  bf16* in16 = arena_.alloc<bf16>(static_cast<size_t>(M) * ldp);
+  OP(launch_cast_bf16(in, in_dim, in16, ldp, M, in_dim, st_), "cast");
+  GemmArgs g;                                    // Linear(in,768) + learned positions (Transformer.py:213-217)
+  g.residual = m.pos; g.ldr = H; g.res_mod = L;
+  g.out_f32 = x32; g.ldo32 = H; g.out_bf16 = x16; g.ldo16 = H;
+  gemm_lin(in16, ldp, M, m.in, g);
+  enc_layers(m.layers, x32, x16, U, L, H, cfg_.heads, cfg_.ffn, mask01, -10000.0f, cfg_.eps);
+}
+
+void Engine::cmt_encoder(const CmtW& cw, const float* xq, int Lq, int q_total, int q_off, const float* xkv, int Lk,
+                         int kv_total, int kv_off, int U, float* out32, bf16* out16, int out_total, int out_off) {
+  const int H = cfg_.hidden;
+  const int Mq = U * Lq, Mk = U * Lk;
+  const size_t mark = arena_.mark();
+  float* x = arena_.alloc<float>(static_cast<size_t>(Mq) * H);
+  float* ek = arena_.alloc<float>(static_cast<size_t>(Mk) * H);
+  bf16* qn = arena_.alloc<bf16>(static_cast<size_t>(Mq) * H);
+  bf16* kn = arena_.alloc<bf16>(static_cast<size_t>(Mk) * H);
+  bf16* q = arena_.alloc<bf16>(static_cast<size_t>(Mq) * H);
+  bf16* kv = arena_.alloc<bf16>(static_cast<size_t>(Mk) * 2 * H);
+  bf16* a = arena_.alloc<bf16>(static_cast<size_t>(Mq) * H);
+  bf16* hid = arena_.alloc<bf16>(static_cast<size_t>(Mq) * 4 * H);
+  const float scale = std::sqrt(static_cast<float>(H));
+  OP(launch_cmt_embed(xq, Lq, q_total, q_off, sinusoid_, U, Lq, H, scale, x, st_), "cmt_embed");
+  OP(launch_cmt_embed(xkv, Lk, kv_total, kv_off, sinusoid_, U, Lk, H, scale, ek, st_), "cmt_embed");
+  for (const CmtLayerW& l : cw.layers) {
+    LnArgs nq;
+    nq.in = x; nq.ld_in = H; nq.M = Mq; nq.cseg = H;
+    nq.gamma = l.ln0.g; nq.beta = l.ln0.b; nq.eps = 1e-5f;
+    nq.out_bf16 = qn; nq.ld16 = H;
+    ln(nq);
+    LnArgs nk = nq;                                  // K/V streams use the same layer_norms[0] (:145-148)
+    nk.in = ek; nk.M = Mk; nk.out_bf16 = kn;
+    ln(nk);
+    GemmArgs gq;
+    gq.out_bf16 = q; gq.ldo16 = H;
+    gemm_lin(qn, H, Mq, l.q, gq);
+    GemmArgs gk;
+    gk.out_bf16 = kv; gk.ldo16 = 2 * H;
+    gemm_lin(kn, H, Mk, l.kv, gk);
+    if (!arena_.dry() && first_err_ == cudaSuccess) {
+      count_launch();
+      flops_ += 4.0 * U * static_cast<double>(Lq) * Lk * H;
+      ck(launch_mha(q, H, kv, 2 * H, kv + H, 2 * H, a, H, nullptr, 0.f, U, cw.heads, Lq, Lk, 0.125f, st_), "mha");
+    }
+    GemmArgs go;
+    go.residual = x; go.ldr = H; go.out_f32 = x; go.ldo32 = H;
+    gemm_lin(a, H, Mq, l.o, go);
+    LnArgs n1 = nq;
+    n1.gamma = l.ln1.g; n1.beta = l.ln1.b;
+    ln(n1);
+    GemmArgs g1;
+    g1.act = ACT_GELU; g1.out_bf16 = hid; g1.ldo16 = 4 * H;
+    gemm_lin(qn, H, Mq, l.fc1, g1);
+    GemmArgs g2;
+    g2.residual = x; g2.ldr = H; g2.out_f32 = x; g2.ldo32 = H;
+    gemm_lin(hid, 4 * H, Mq, l.fc2, g2);
+  }
+  LnArgs nf;
+  nf.in = x; nf.ld_in = H; nf.M = Mq; nf.cseg = H;
+  nf.gamma = cw.final_ln.g; nf.beta = cw.final_ln.b; nf.eps = 1e-5f;
+  nf.out_f32 = out32; nf.ld32 = H; nf.out_bf16 = out16; nf.ld16 = H;
+  nf.rows_in = Lq; nf.rows_out = out_total; nf.row_off = out_off;
+  ln(nf);
+  arena_.release(mark);
+}
+
+void Engine::pool_head(const float* x32, const bf16* x16, const float* mask01, int U, int L, float* logits) {
+  const int H = cfg_.hidden;
+  bf16* th = arena_.alloc<bf16>(static_cast<size_t>(U) * L * H);
+  GemmArgs g;
+  g.act = ACT_TANH; g.out_bf16 = th; g.ldo16 = H;
+  gemm_lin(x16, H, U * L, pool_.P, g);
+  OP(launch_pool_classify(x32, th, mask01, pool_.wv, pool_.bv, pool_.wc, pool_.bc, U, L, H, cfg_.num_labels, logits, st_),
+     "pool_classify");
+}
+
+void Engine::multimodal_body(const int64_t* ids, const int64_t* mask, const int64_t* sep, const float* audio,
+                             const float* audio_mask, const float* vision, const float* vision_mask, const int64_t* idx,
+                             int U, int L, float* logits) {
+  const fmmt_config& c = cfg_;
+  const int H = c.hidden, D = c.text_hidden, M = U * L;
+  const int Lt = c.text_len, La = c.audio_len, Lv = c.vision_len;
+  // ---- text (src/models.py:99-107)
+  int* pos = arena_.alloc<int>(M);
+  float* tx32 = arena_.alloc<float>(static_cast<size_t>(M) * D);
+  bf16* tx16 = arena_.alloc<bf16>(static_cast<size_t>(M) * D);
+  float* tmask = arena_.alloc<float>(M);
+  if (!arena_.dry() && first_err_ == cudaSuccess) {
+    count_launch(2);
+    ck(launch_text_embed(ids, pos, U, L, c.text_kind == FMMT_TEXT_ROBERTA, c.pad_id, text_.word, text_.pos, text_.type0,
+                         c.max_pos, c.vocab_size, text_.emb_ln.g, text_.emb_ln.b, c.text_eps, D, tx32, tx16, st_),
+       "text_embed");
+  }
+  OP(launch_cast_i64_f32(mask, tmask, M, st_), "mask cast");
+  {
+    const size_t mk = arena_.mark();
+    enc_layers(text_.layers, tx32, tx16, U, L, D, c.text_heads, c.text_ffn, tmask, -3.4028234663852886e38f, c.text_eps);
+    arena_.release(mk);
+  }
+  float* t768 = arena_.alloc<float>(static_cast<size_t>(M) * H);
+  GemmArgs gt;
+  gt.out_f32 = t768; gt.ldo32 = H;
+  gemm_lin(tx16, D, M, text_.out, gt);
+  capture("mm.text768", t768, static_cast<size_t>(M) * H);
+  float* txt = arena_.alloc<float>(static_cast<size_t>(U) * Lt * H);
+  float* txt_mask = arena_.alloc<float>(static_cast<size_t>(U) * Lt);
+  OP(launch_span_extract(t768, sep, idx, U, L, H, Lt, c.text_kind == FMMT_TEXT_ROBERTA ? 2 : 1, txt, txt_mask, st_),
+     "span_extract");
+  capture("mm.text", txt, static_cast<size_t>(U) * Lt * H);
+  // ---- audio / vision self-attention encoders (src/models.py:154-166)
+  float* ax32 = arena_.alloc<float>(static_cast<size_t>(U) * La * H);
+  bf16* ax16 = arena_.alloc<bf16>(static_cast<size_t>(U) * La * H);
+  float* vx32 = arena_.alloc<float>(static_cast<size_t>(U) * Lv * H);
+  bf16* vx16 = arena_.alloc<bf16>(static_cast<size_t>(U) * Lv * H);
+  {
+    const size_t mk = arena_.mark();
+    meld_encoder(audio_, audio, c.audio_dim, U, La, audio_mask, ax32, ax16);
+    arena_.release(mk);
+    meld_encoder(vision_, vision, c.vision_dim + c.num_labels, U, Lv, vision_mask, vx32, vx16);
+    arena_.release(mk);
+  }
+  capture("mm.audio", ax32, static_cast<size_t>(U) * La * H);
+  capture("mm.vision", vx32, static_cast<size_t>(U) * Lv * H);
+  // ---- cross-modal fusion (src/models.py:169-179); concat along time by writing slices of one buffer
+  const int Lta = Lt + La, Ltot = Lta + Lv;
+  float* ta = arena_.alloc<float>(static_cast<size_t>(U) * Lta * H);
+  float* fused = arena_.alloc<float>(static_cast<size_t>(U) * Ltot * H);
+  bf16* fused16 = arena_.alloc<bf16>(static_cast<size_t>(U) * Ltot * H);
+  float* fmask = arena_.alloc<float>(static_cast<size_t>(U) * Ltot);
+  cmt_encoder(cmt_ta_, txt, Lt, Lt, 0, ax32, La, La, 0, U, ta, nullptr, Lta, 0);
+  cmt_encoder(cmt_ta_, ax32, La, La, 0, txt, Lt, Lt, 0, U, ta, nullptr, Lta, Lt);
+  capture("mm.ta", ta, static_cast<size_t>(U) * Lta * H);
+  cmt_encoder(cmt_tav_, ta, Lta, Lta, 0, vx32, Lv, Lv, 0, U, fused, fused16, Ltot, 0);
+  cmt_encoder(cmt_tav_, vx32, Lv, Lv, 0, ta, Lta, Lta, 0, U, fused, fused16, Ltot, Lta);
+  capture("mm.fused", fused, static_cast<size_t>(U) * Ltot * H);
+  OP(launch_concat_masks(txt_mask, Lt, audio_mask, La, vision_mask, Lv, fmask, U, st_), "concat_masks");
+  pool_head(fused, fused16, fmask, U, Ltot, logits);
+}
+
+int Engine::multimodal_forward(const int64_t* ids, const int64_t* mask, const int64_t* sep, const float* audio,
+                               const float* audio_mask, const float* vision, const float* vision_mask,
+                               const int64_t* idx, int U, int L, float* logits, cudaStream_t st) {
+  if (cfg_.model != FMMT_MODEL_MULTIMODAL) return set_error(FMMT_ERR_STATE, "handle is not a multimodal model");
+  if (!ids || !mask || !sep || !audio || !audio_mask || !vision || !vision_mask || !idx || !logits)
+    return set_error(FMMT_ERR_INVALID, "fmmt_multimodal_forward: null pointer");
+  if (U <= 0 || L <= 0 || L > cfg_.max_pos - (cfg_.text_kind == FMMT_TEXT_ROBERTA ? cfg_.pad_id + 1 : 0))
+    return set_error(FMMT_ERR_INVALID, "fmmt_multimodal_forward: bad U / L (L exceeds the position table)");
+  return run([&] { multimodal_body(ids, mask, sep, audio, audio_mask, vision, vision_mask, idx, U, L, logits); }, st);
+}
+
+void Engine::unimodal_body(const float* inputs, const float* mask, int U, float* logits) {
+  const fmmt_config& c = cfg_;
+  const int H = c.hidden, Lv = c.vision_len;
+  float* x32 = arena_.alloc<float>(static_cast<size_t>(U) * Lv * H);
+  bf16* x16 = arena_.alloc<bf16>(static_cast<size_t>(U) * Lv * H);
+  const size_t mk = arena_.mark();
+  meld_encoder(vision_, inputs, c.vision_dim, U, Lv, mask, x32, x16);
+  arena_.release(mk);
+  pool_head(x32, x16, mask, U, Lv, logits);
+}
+
+int Engine::unimodal_forward(const float* inputs, const float* mask, int U, float* logits, cudaStream_t st) {
+  if (cfg_.model != FMMT_MODEL_UNIMODAL) return set_error(FMMT_ERR_STATE, "handle is not a unimodal model");
+  if (!inputs || !mask || !logits || U <= 0) return set_error(FMMT_ERR_INVALID, "fmmt_unimodal_forward: bad arguments");
+  return run([&] { unimodal_body(inputs, mask, U, logits); }, st);
+}
+
+}  // namespace fmmt

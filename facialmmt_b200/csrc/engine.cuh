@@ -1,0 +1,221 @@
+// Engine: owns packed device weights + a workspace arena and sequences the kernels of one forward on a stream.
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+
+#include <map>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "facialmmt_b200.h"
+#include "gemm.cuh"
+#include "ops.cuh"
+
+namespace fmmt {
+
+typedef __nv_bfloat16 bf16;
+
+struct HostTensor {
+  std::vector<float> data;
+  std::vector<int64_t> shape;
+  int64_t numel() const {
+    int64_t n = 1;
+    for (auto d : shape) n *= d;
+    return n;
+  }
+};
+
+// Linear weight on device: bf16 [N, ld] (K contiguous, ld = K rounded up to 8, zero padded) + fp32 bias.
+struct Lin {
+  bf16* w = nullptr;
+  float* b = nullptr;
+  int N = 0, K = 0, ld = 0;
+};
+struct Norm {
+  float* g = nullptr;
+  float* b = nullptr;
+  int C = 0;
+};
+
+struct SwinBlockW {
+  Norm ln1, ln2;
+  Lin qkv, proj, fc1, fc2;
+  float* bias_exp = nullptr;  // [heads, N, N]
+  int shift = 0;
+};
+struct SwinStageW {
+  int R = 0, C = 0, heads = 0, ws = 0, N = 0, nW = 0;
+  int* win_map[2] = {nullptr, nullptr};  // [T] window-order row -> token, for shift 0 and shift ws/2
+  int8_t* rid = nullptr;                 // [nW, N] region ids for shifted blocks
+  std::vector<SwinBlockW> blocks;
+  bool has_merge = false;
+  int* merge_map = nullptr;  // [T/4, 4]
+  Norm merge_ln;
+  Lin merge;
+};
+struct SwinW {
+  Lin patch;  // [C0, 48]
+  Norm patch_ln;
+  std::vector<SwinStageW> stages;
+  Norm head_ln;
+  Lin head;  // [feat, R*R*C] with BatchNorm folded in
+  float* w1t = nullptr;  // [feat, hidden]
+  float* b1 = nullptr;
+  float* w2 = nullptr;   // [labels, hidden]
+  float* b2 = nullptr;
+};
+
+// Post-LN encoder layer (HF BERT/RoBERTa layer and MELDTrans TransformerEnoderLayer share this structure).
+struct EncLayerW {
+  Lin qkv, o, fc1, fc2;
+  Norm ln1, ln2;
+};
+struct CmtLayerW {
+  Lin q, kv, o, fc1, fc2;
+  Norm ln0, ln1;
+};
+struct CmtW {
+  std::vector<CmtLayerW> layers;
+  Norm final_ln;
+  int heads = 12;
+};
+struct MeldEncW {
+  Lin in;                 // audio_linear / vision_linear / modality_linear
+  float* pos = nullptr;   // [max_len, H]
+  int max_len = 0;
+  std::vector<EncLayerW> layers;
+};
+struct PoolW {
+  Lin P;        // bias = P.bias + Q(query_vector)
+  float* wv = nullptr;
+  float bv = 0.f;
+  float* wc = nullptr;  // [labels, H]
+  float* bc = nullptr;
+};
+struct TextW {
+  float* word = nullptr;
+  float* pos = nullptr;
+  float* type0 = nullptr;
+  Norm emb_ln;
+  std::vector<EncLayerW> layers;
+  Lin out;  // text_linear
+};
+
+class Arena {
+ public:
+  void begin(bool dry, char* base, size_t cap) { dry_ = dry; base_ = base; cap_ = cap; off_ = 0; peak_ = 0; }
+  template <typename T>
+  T* alloc(size_t n) {
+    off_ = (off_ + 255) & ~static_cast<size_t>(255);
+    char* p = base_ + off_;
+    off_ += n * sizeof(T);
+    if (off_ > peak_) peak_ = off_;
+    return reinterpret_cast<T*>(p);
+  }
+  size_t mark() const { return off_; }
+  void release(size_t m) { off_ = m; }
+  size_t peak() const { return peak_; }
+  bool dry() const { return dry_; }
+  size_t cap() const { return cap_; }
+
+ private:
+  bool dry_ = true;
+  char* base_ = nullptr;
+  size_t cap_ = 0, off_ = 0, peak_ = 0;
+};
+
+class Engine {
+ public:
+  explicit Engine(const fmmt_config& cfg);
+  ~Engine();
+  int load_weight(const char* key, const float* data, const int64_t* shape, int ndim);
+  int finalize();
+  int swin_forward(const float* frames, int F, const float* gumbel, float tau, float* logits, float* probs,
+                   float* importance, float* feat, cudaStream_t st);
+  int multimodal_forward(const int64_t* ids, const int64_t* mask, const int64_t* sep, const float* audio,
+                         const float* audio_mask, const float* vision, const float* vision_mask, const int64_t* idx,
+                         int U, int L, float* logits, cudaStream_t st);
+  int unimodal_forward(const float* inputs, const float* mask, int U, float* logits, cudaStream_t st);
+  int set_capture(const char* name, float* dst, int64_t count);
+  double flops(bool reset) { double f = flops_; if (reset) flops_ = 0; return f; }
+  int64_t device_bytes() const { return static_cast<int64_t>(weight_bytes_ + ws_cap_); }
+  const std::string& error() const { return err_; }
+
+ private:
+  // ---- weight packing
+  const HostTensor* find(const std::string& key);
+  const HostTensor& need(const std::string& key);
+  template <typename T> T* dev_alloc(size_t n);
+  float* up_f32(const float* src, size_t n);
+  bf16* up_bf16(const float* src, int rows, int cols, int ld);
+  Lin make_lin(const float* w, const float* b, int N, int K);
+  Lin lin(const std::string& prefix, bool bias = true);
+  Norm norm(const std::string& prefix);
+  EncLayerW enc_layer(const std::string& qkv_prefix, const std::string& o_prefix, const std::string& ln1_prefix,
+                      const std::string& fc1_prefix, const std::string& fc2_prefix, const std::string& ln2_prefix,
+                      int H);
+  void pack_swin();
+  void pack_text();
+  void pack_meld(MeldEncW& m, const std::string& lin_prefix, const std::string& enc_prefix, int layers, int in_dim,
+                 int max_len);
+  void pack_cmt(CmtW& c, const std::string& prefix, int layers, int heads);
+  void pack_pool(const std::string& prefix, const std::string& cls_prefix);
+  void build_sinusoid(int max_len);
+
+  // ---- op wrappers (no-ops while sizing the workspace)
+  void gemm(GemmArgs a);
+  void gemm_lin(const bf16* A, int lda, int M, const Lin& l, GemmArgs ep);
+  void ln(LnArgs a);
+  void ck(cudaError_t e, const char* what);
+  void capture(const std::string& name, const float* src, size_t count, size_t dst_off = 0);
+
+  // ---- forward bodies (run twice the first time a size is seen: dry sizing pass, then real)
+  void swin_body(const float* frames, int F, const float* gumbel, float tau, float* logits, float* probs,
+                 float* importance, float* feat);
+  void swin_early(const float* frames, int f0, int nf, float* x2_out);
+  void swin_late(float* x2, int f0, int nf, bf16* feat_ln);
+  void swin_block(const SwinStageW& sw, const SwinBlockW& bw, float* x, int nf, bf16* h, bf16* qkv, bf16* a, bf16* hid);
+  void enc_layers(const std::vector<EncLayerW>& layers, float* x32, bf16* x16, int U, int L, int H, int heads, int ffn,
+                  const float* mask01, float mask_neg, float eps);
+  void meld_encoder(const MeldEncW& m, const float* in, int in_dim, int U, int L, const float* mask01, float* x32,
+                    bf16* x16);
+  void cmt_encoder(const CmtW& c, const float* xq, int Lq, int q_total, int q_off, const float* xkv, int Lk, int kv_total,
+                   int kv_off, int U, float* out32, bf16* out16, int out_total, int out_off);
+  void pool_head(const float* x32, const bf16* x16, const float* mask01, int U, int L, float* logits);
+  void multimodal_body(const int64_t* ids, const int64_t* mask, const int64_t* sep, const float* audio,
+                       const float* audio_mask, const float* vision, const float* vision_mask, const int64_t* idx, int U,
+                       int L, float* logits);
+  void unimodal_body(const float* inputs, const float* mask, int U, float* logits);
+  template <typename Fn> int run(Fn&& body, cudaStream_t st);
+
+  fmmt_config cfg_;
+  bool finalized_ = false;
+  std::unordered_map<std::string, HostTensor> host_;
+  std::vector<void*> dev_ptrs_;
+  size_t weight_bytes_ = 0;
+  SwinW swin_;
+  TextW text_;
+  MeldEncW audio_, vision_;
+  CmtW cmt_ta_, cmt_tav_;
+  PoolW pool_;
+  float* sinusoid_ = nullptr;  // [max_len+1, H]
+  int sinusoid_len_ = 0;
+
+  Arena arena_;
+  char* ws_ = nullptr;
+  size_t ws_cap_ = 0;
+  cudaStream_t st_ = nullptr;
+  cudaError_t first_err_ = cudaSuccess;
+  std::string err_;
+  double flops_ = 0;
+  struct Cap { float* dst; int64_t count; };
+  std::map<std::string, Cap> caps_;
+};
+
+extern thread_local std::string g_last_error;
+int set_error(int code, const std::string& msg);
+void count_launch(int n = 1);
+
+}  // namespace fmmt

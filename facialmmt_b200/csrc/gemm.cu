@@ -32,6 +32,7 @@ struct GemmKernelParams {
   int act;
   const float* residual;
   int ldr;
+  int res_mod;
   float* out_f32;
   int ldo32;
   __nv_bfloat16* out_bf16;
@@ -166,6 +167,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
           dest = q * p.rows_out + p.row_off + (dest - q * p.rows_in);
         }
       }
+      const long long rrow = (p.res_mod > 0) ? (dest % p.res_mod) : dest;
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(warp * 32) << 16) +
                              static_cast<uint32_t>(acc * ACC_STRIDE);
       for (int c = 0; c < p.block_n; c += 32) {
@@ -191,7 +193,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
             for (int j = 0; j < 32; ++j) x[j] = apply_act(x[j], p.act);
           }
           if (p.residual != nullptr) {
-            const float4* r4 = reinterpret_cast<const float4*>(p.residual + dest * p.ldr + gc);
+            const float4* r4 = reinterpret_cast<const float4*>(p.residual + rrow * p.ldr + gc);
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
               const float4 r = r4[j];
@@ -216,7 +218,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
             float y = x[j];
             if (p.bias != nullptr) y += p.bias[gc + j];
             y = apply_act(y, p.act);
-            if (p.residual != nullptr) y += p.residual[dest * p.ldr + gc + j];
+            if (p.residual != nullptr) y += p.residual[rrow * p.ldr + gc + j];
             if (p.out_f32 != nullptr) p.out_f32[dest * p.ldo32 + gc + j] = y;
             if (p.out_bf16 != nullptr) p.out_bf16[dest * p.ldo16 + gc + j] = __float2bfloat16(y);
           }
@@ -328,7 +330,7 @@ cudaError_t launch_gemm(const GemmArgs& a, cudaStream_t stream) {
   p.n_tiles = (a.N + p.block_n - 1) / p.block_n;
   p.num_kb = (a.K + BK - 1) / BK;
   p.bias = a.bias; p.act = a.act;
-  p.residual = a.residual; p.ldr = a.ldr;
+  p.residual = a.residual; p.ldr = a.ldr; p.res_mod = a.res_mod;
   p.out_f32 = a.out_f32; p.ldo32 = a.ldo32;
   p.out_bf16 = a.out_bf16; p.ldo16 = a.ldo16;
   p.row_map = a.row_map; p.map_period = a.map_period;

@@ -23,6 +23,7 @@ struct GemmArgs {
   int act = ACT_NONE;
   const float* residual = nullptr;  // fp32 [*, ldr], indexed by dest row
   int ldr = 0;
+  int res_mod = 0;                  // >0: residual row = dest % res_mod (broadcast table, e.g. learned positions)
   float* out_f32 = nullptr;         // fp32 [*, ldo32], indexed by dest row
   int ldo32 = 0;
   __nv_bfloat16* out_bf16 = nullptr;  // bf16 [*, ldo16], indexed by dest row

@@ -3,10 +3,13 @@
  * The reference (NUSTM/FacialMMT) has no FFI: its boundary for this path is the Python nn.Module API of
  * src/models.py (SwinForAffwildClassification :14-37, MultiModalTransformerForClassification :41-188,
  * meld_utt_transformer :192-223) plus the eval glue of train.py:169-234. Each entry point below names the
- * reference call it replaces. All pointers are plain device (or, where stated, host) pointers; no torch types.
+ * reference call it replaces. All pointers are plain device pointers unless marked HOST; no torch types.
  * Every function returns 0 on success and a negative code on failure; fmmt_last_error() gives the message.
- * Calls are asynchronous on the given cudaStream_t (passed as void*), and never synchronise the device unless
- * stated. A handle belongs to one device and is not re-entrant.
+ * Calls are asynchronous on the given cudaStream_t (passed as void*) and never synchronise the device, except
+ * fmmt_finalize and the first forward at a new (larger) problem size, which (re)allocates the workspace.
+ * A handle belongs to one device and is not re-entrant. The library owns packed weights + workspace only; it never
+ * retains caller pointers beyond a call, and writes results into caller-allocated buffers.
+ * There is NO CPU fallback: without an sm_100 device every compute entry point fails with FMMT_ERR_CUDA.
  */
 #ifndef FACIALMMT_B200_H
 #define FACIALMMT_B200_H
@@ -24,10 +27,9 @@ extern "C" {
 #endif
 
 #define FMMT_OK 0
-#define FMMT_ERR_INVALID (-1)   /* bad shape / pointer / alignment (the reference would assert) */
-#define FMMT_ERR_CUDA (-2)      /* CUDA runtime / driver error */
-#define FMMT_ERR_STATE (-3)     /* handle not finalized, weight missing, ... */
-#define FMMT_ERR_NOGPU (-4)     /* no sm_100 device: there is NO CPU fallback */
+#define FMMT_ERR_INVALID (-1) /* bad shape / pointer / alignment (the reference would assert) */
+#define FMMT_ERR_CUDA (-2)    /* CUDA runtime / driver error */
+#define FMMT_ERR_STATE (-3)   /* handle not finalized, weight missing, wrong model kind, ... */
 
 /* Activation codes for fmmt_op_gemm. */
 #define FMMT_ACT_NONE 0
@@ -35,10 +37,89 @@ extern "C" {
 #define FMMT_ACT_RELU 2
 #define FMMT_ACT_TANH 3
 
+/* Which reference module a handle implements. */
+#define FMMT_MODEL_SWIN_CLS 1   /* src/models.py:14-37   SwinForAffwildClassification */
+#define FMMT_MODEL_MULTIMODAL 2 /* src/models.py:41-188  MultiModalTransformerForClassification */
+#define FMMT_MODEL_UNIMODAL 3   /* src/models.py:192-223 meld_utt_transformer */
+
+#define FMMT_TEXT_ROBERTA 0
+#define FMMT_TEXT_BERT 1
+
+typedef struct fmmt_handle fmmt_handle;
+
+/* Dimensions only (mirrors swin_conf.yaml, main.py:62-83 and the HF roberta-large / bert-large configs). */
+typedef struct fmmt_config {
+  int32_t model; /* FMMT_MODEL_* */
+  /* Swin-cls */
+  int32_t img_size, patch_size, in_chans, embed_dim, num_stages;
+  int32_t depths[4], num_heads[4];
+  int32_t window_size, mlp_ratio; /* mlp_ratio as integer (4) */
+  int32_t feat_dim, head_hidden, num_labels;
+  int32_t swin_chunk;      /* frames per pass through stages 1-2 (L2-resident working set); 0 = default */
+  int32_t swin_chunk_late; /* frames per pass through stages 3-4; 0 = default */
+  /* text encoder */
+  int32_t text_kind, vocab_size, text_hidden, text_layers, text_heads, text_ffn, max_pos, type_vocab, pad_id;
+  float text_eps;
+  /* fusion */
+  int32_t hidden, heads, ffn, audio_dim, vision_dim, audio_layers, vision_layers;
+  int32_t cmt_layers_ta, cmt_heads_ta, cmt_layers_tav, cmt_heads_tav;
+  int32_t text_len, audio_len, vision_len;
+  float eps;
+} fmmt_config;
+
 FMMT_API const char* fmmt_last_error(void);
 FMMT_API const char* fmmt_version(void);
 /* Number of kernels this library has launched since load (bench.py's gpu_launches). */
 FMMT_API int64_t fmmt_launch_count(void);
+
+/* ---- lifecycle (replaces nn.Module construction + load_state_dict / torch.load, train.py:428-432) ---- */
+FMMT_API int fmmt_create(const fmmt_config* cfg, fmmt_handle** out);
+FMMT_API void fmmt_destroy(fmmt_handle* h);
+/* Stage one tensor of the reference state_dict under its reference key name. `data` is a HOST pointer to contiguous
+ * fp32; shape/ndim as in the state_dict. Unknown keys are rejected with FMMT_ERR_INVALID (integer buffers such as
+ * relative_position_index / num_batches_tracked / position_ids are recomputed and must not be passed). */
+FMMT_API int fmmt_load_weight(fmmt_handle* h, const char* ref_key, const float* data, const int64_t* shape, int ndim);
+/* Pack to device: bf16 K-major weights, fused QKV, BatchNorm folded into Linear(37632,512), relative-position bias
+ * expanded to (heads,49,49), shift-region ids, window/merge gather maps, sinusoid table. Synchronous. */
+FMMT_API int fmmt_finalize(fmmt_handle* h);
+
+/* ---- model-level forwards ---- */
+
+/* SwinForAffwildClassification.forward (src/models.py:26-37) on `n_frames` frames, fp32 NCHW (F,3,224,224).
+ * gumbel: (F,labels) explicit noise g so that probs = softmax((logits+g)/tau) == F.gumbel_softmax (NULL: g = 0).
+ * Outputs (any may be NULL): logits (F,labels) raw; probs (F,labels); importance (F) = sum_c p_c^2 (train.py:183-184);
+ * feat (F,feat_dim) = backbone output after BatchNorm. */
+FMMT_API int fmmt_swin_forward(fmmt_handle* h, const float* frames, int n_frames, const float* gumbel, float tau,
+                               float* logits, float* probs, float* importance, float* feat, void* stream);
+
+/* Frame filter + compaction of the eval glue (train.py:185-232). frame_off: device int32 [U+1], prefix sums of the
+ * per-utterance frame counts into `probs` (total_frames rows). per_utterance=1: each utterance decides the
+ * "no frame passes" fallback on its own (== the reference at its batch size 1); 0: literal whole-batch decision.
+ * out_v: (U,Lv,D+labels), out_mask: (U,Lv). scratch: device int32[1] (needed when per_utterance=0). */
+FMMT_API int fmmt_filter_pack(const float* vision, const float* vision_mask, const int32_t* frame_off, int total_frames,
+                              const float* probs, float threshold, int per_utterance, float* out_v, float* out_mask,
+                              int32_t* scratch, int U, int Lv, int D, int labels, void* stream);
+
+/* MultiModalTransformerForClassification.forward (src/models.py:95-188). ids/mask/sep_mask: int64 (U,L);
+ * audio fp32 (U,La,audio_dim); audio_mask fp32 (U,La); vision fp32 (U,Lv,vision_dim+labels); vision_mask fp32 (U,Lv);
+ * idx_in_dia int64 (U); logits fp32 (U,labels). */
+FMMT_API int fmmt_multimodal_forward(fmmt_handle* h, const int64_t* ids, const int64_t* mask, const int64_t* sep_mask,
+                                     const float* audio, const float* audio_mask, const float* vision,
+                                     const float* vision_mask, const int64_t* idx_in_dia, int U, int L, float* logits,
+                                     void* stream);
+
+/* meld_utt_transformer.forward (src/models.py:209-223): inputs fp32 (U,Lv,vision_dim), utt_mask fp32 (U,Lv). */
+FMMT_API int fmmt_unimodal_forward(fmmt_handle* h, const float* inputs, const float* utt_mask, int U, float* logits,
+                                   void* stream);
+
+/* Stage-wise parity hook: during the next forwards, copy the named fp32 intermediate into `dst` (device, `count`
+ * floats). name == NULL clears all captures. Names: swin.patch_embed, swin.layer<l>.block<b>, swin.feat,
+ * mm.text768, mm.text, mm.audio, mm.vision, mm.ta, mm.fused. */
+FMMT_API int fmmt_set_capture(fmmt_handle* h, const char* name, float* dst, int64_t count);
+/* Algorithmic FLOPs (2*MAC of every GEMM/attention launched) accumulated by the handle since the last reset. */
+FMMT_API double fmmt_flops(fmmt_handle* h, int reset);
+/* Bytes of device memory held by the handle (weights + workspace). */
+FMMT_API int64_t fmmt_device_bytes(fmmt_handle* h);
 
 /* ---- operator-level entry points (one CUDA kernel each); used by the per-kernel parity tests ---- */
 
@@ -48,6 +129,21 @@ FMMT_API int64_t fmmt_launch_count(void);
 FMMT_API int fmmt_op_gemm(const void* A_bf16, int lda, const void* W_bf16, int ldw, int M, int N, int K,
                           const float* bias, int act, const float* residual, int ldr, float* out_f32, int ldo32,
                           void* out_bf16, int ldo16, const int* row_map, int map_period, int block_n, void* stream);
+
+/* LayerNorm over rows gathered from `nseg` segments (see csrc/ops.cuh LnArgs); biased variance, eps inside sqrt. */
+FMMT_API int fmmt_op_layernorm(const float* in, int ld_in, int M, int nseg, int cseg, const int* map, int map_period,
+                               int src_period, const float* gamma, const float* beta, float eps, float* out_f32,
+                               int ld32, void* out_bf16, int ld16, void* stream);
+
+/* Swin window attention core (Swin_Transformer.py:119-141): qkv bf16 [num_windows*N, 3C] in window order,
+ * bias fp32 [heads,N,N], rid int8 [nW,N] shift-region ids or NULL, out bf16 [num_windows*N, C]. head_dim = 32. */
+FMMT_API int fmmt_op_window_attention(const void* qkv_bf16, void* out_bf16, const float* bias, const int8_t* rid,
+                                      int num_windows, int nW, int heads, int C, int N, float scale, void* stream);
+
+/* Multi-head attention core, head_dim 64: softmax(scale * q k^T + (1 - key_mask) * mask_neg) v.
+ * q rows (b*Lq+i), k/v rows (b*Lk+j), head h at columns [64h, 64h+64). key_mask fp32 (B,Lk) of 0/1 or NULL. */
+FMMT_API int fmmt_op_mha(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv, void* out, int ldo,
+                         const float* key_mask, float mask_neg, int B, int H, int Lq, int Lk, float scale, void* stream);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,126 @@
+"""Per-kernel parity (C ABI -> CUDA) against plain fp32 torch restatements of the same op on the same bf16 inputs."""
+import math
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _gen(seed):
+    return torch.Generator(device="cpu").manual_seed(seed)
+
+
+@pytest.mark.parametrize("M,C", [(1000, 96), (37, 192), (513, 384), (100, 768), (64, 1024), (9, 1536)])
+def test_layernorm_plain(lib, M, C):
+    from facialmmt_b200._lib import check, cur_stream, ptr
+    g = _gen(M + C)
+    x = (torch.randn(M, C, generator=g) * 3 + 1).cuda()
+    w, b = torch.randn(C, generator=g).cuda(), torch.randn(C, generator=g).cuda()
+    o32 = torch.empty(M, C, device="cuda")
+    o16 = torch.empty(M, C, device="cuda", dtype=torch.bfloat16)
+    check(lib.fmmt_op_layernorm(ptr(x), C, M, 1, C, None, 0, 0, ptr(w), ptr(b), 1e-5, ptr(o32), C, ptr(o16), C,
+                                cur_stream()))
+    ref = torch.nn.functional.layer_norm(x, (C,), w, b, 1e-5)
+    assert (o32 - ref).abs().max().item() < 2e-5 * ref.abs().max().item() + 1e-5
+    assert (o16.float() - ref).abs().max().item() < 1e-2 * ref.abs().max().item()
+
+
+def test_layernorm_window_gather_and_merge(lib):
+    from facialmmt_b200._lib import check, cur_stream, ptr
+    from oracle.facialmmt_oracle import swin_window_index
+    g = _gen(5)
+    Fn, R, C = 3, 14, 96
+    T = R * R
+    x = torch.randn(Fn * T, C, generator=g).cuda()
+    w, b = torch.randn(C, generator=g).cuda(), torch.randn(C, generator=g).cuda()
+    idx = swin_window_index(R, 7, 3).to(torch.int32).cuda()
+    o = torch.empty(Fn * T, C, device="cuda")
+    check(lib.fmmt_op_layernorm(ptr(x), C, Fn * T, 1, C, ptr(idx), T, T, ptr(w), ptr(b), 1e-5, ptr(o), C, None, 0,
+                                cur_stream()))
+    ref = torch.nn.functional.layer_norm(x, (C,), w, b, 1e-5).view(Fn, T, C)[:, idx.long()].reshape(Fn * T, C)
+    assert (o - ref).abs().max().item() < 1e-4
+    # patch-merge style: 4 segments from 4 source rows
+    R2 = R // 2
+    mm = torch.tensor([[(2 * y) * R + 2 * xx, (2 * y + 1) * R + 2 * xx, (2 * y) * R + 2 * xx + 1, (2 * y + 1) * R + 2 * xx + 1]
+                       for y in range(R2) for xx in range(R2)], dtype=torch.int32).cuda()
+    w4, b4 = torch.randn(4 * C, generator=g).cuda(), torch.randn(4 * C, generator=g).cuda()
+    o4 = torch.empty(Fn * R2 * R2, 4 * C, device="cuda")
+    check(lib.fmmt_op_layernorm(ptr(x), C, Fn * R2 * R2, 4, C, ptr(mm), R2 * R2, T, ptr(w4), ptr(b4), 1e-5, ptr(o4),
+                                4 * C, None, 0, cur_stream()))
+    xv = x.view(Fn, R, R, C)
+    cat = torch.cat([xv[:, 0::2, 0::2], xv[:, 1::2, 0::2], xv[:, 0::2, 1::2], xv[:, 1::2, 1::2]], -1).reshape(-1, 4 * C)
+    ref4 = torch.nn.functional.layer_norm(cat, (4 * C,), w4, b4, 1e-5)
+    assert (o4 - ref4).abs().max().item() < 1e-4
+
+
+@pytest.mark.parametrize("R,heads,shift", [(56, 3, 0), (56, 3, 3), (28, 6, 3), (14, 12, 3), (14, 12, 0), (7, 24, 0)])
+def test_window_attention(lib, R, heads, shift):
+    from facialmmt_b200._lib import check, cur_stream, ptr
+    from oracle.facialmmt_oracle import swin_rel_bias, swin_shift_mask
+    g = _gen(R * 100 + heads + shift)
+    Fn, ws = 2, 7
+    N, C = ws * ws, heads * 32
+    nW = (R // ws) ** 2
+    B_ = Fn * nW
+    qkv = (torch.randn(B_ * N, 3 * C, generator=g)).to(torch.bfloat16)
+    table = torch.randn((2 * ws - 1) ** 2, heads, generator=g)
+    bias = swin_rel_bias(table, ws).contiguous()
+    rid = None
+    if shift:
+        def region(p):
+            return 0 if p < R - ws else (1 if p < R - shift else 2)
+        r = torch.tensor([[3 * region(a) + region(b) for b in range(R)] for a in range(R)])
+        n = R // ws
+        rid = r.view(n, ws, n, ws).permute(0, 2, 1, 3).reshape(nW, N).to(torch.int8).contiguous()
+    out = torch.zeros(B_ * N, C, device="cuda", dtype=torch.bfloat16)
+    scale = 32 ** -0.5
+    qd, bd = qkv.cuda(), bias.cuda()
+    rd = rid.cuda() if rid is not None else None
+    check(lib.fmmt_op_window_attention(ptr(qd), ptr(out), ptr(bd), ptr(rd), B_, nW, heads, C, N, scale, cur_stream()))
+    torch.cuda.synchronize()
+    x = qkv.float().view(B_, N, 3, heads, 32).permute(2, 0, 3, 1, 4)
+    att = (x[0] * scale) @ x[1].transpose(-1, -2) + bias[None]
+    if shift:
+        att = (att.view(Fn, nW, heads, N, N) + swin_shift_mask(R, ws, shift)[None, :, None]).view(-1, heads, N, N)
+    ref = (torch.softmax(att, -1) @ x[2]).transpose(1, 2).reshape(B_ * N, C)
+    err = (out.float().cpu() - ref).abs().max().item()
+    assert err < 3e-2, err     # P and the output are rounded to bf16 (rel 2^-8) on O(1..3) values
+
+
+@pytest.mark.parametrize("B,H,Lq,Lk,masked", [(2, 12, 38, 160, False), (3, 12, 160, 38, False), (2, 12, 198, 160, False),
+                                               (2, 12, 160, 198, False), (2, 16, 128, 128, True), (1, 16, 512, 512, True),
+                                               (3, 12, 160, 160, True), (2, 12, 7, 5, True)])
+def test_mha(lib, B, H, Lq, Lk, masked):
+    from facialmmt_b200._lib import check, cur_stream, ptr
+    g = _gen(B * 1000 + Lq + Lk)
+    E = H * 64
+    q = torch.randn(B * Lq, E, generator=g).to(torch.bfloat16)
+    kv = torch.randn(B * Lk, 2 * E, generator=g).to(torch.bfloat16)
+    mask = None
+    if masked:
+        mask = torch.ones(B, Lk)
+        for b in range(B):
+            mask[b, max(1, Lk - 3 - 17 * b):] = 0
+        if B > 2:
+            mask[2] = 0          # fully masked row: additive mask -> plain softmax over raw scores
+    out = torch.zeros(B * Lq, E, device="cuda", dtype=torch.bfloat16)
+    qd, kvd = q.cuda(), kv.cuda()
+    md = mask.cuda() if masked else None
+    check(lib.fmmt_op_mha(ptr(qd), E, ptr(kvd), 2 * E, c_off(kvd, E), 2 * E, ptr(out), E, ptr(md), -10000.0, B, H, Lq,
+                          Lk, 0.125, cur_stream()))
+    torch.cuda.synchronize()
+    qf = q.float().view(B, Lq, H, 64).transpose(1, 2)
+    kf = kv.float()[:, :E].reshape(B, Lk, H, 64).transpose(1, 2)
+    vf = kv.float()[:, E:].reshape(B, Lk, H, 64).transpose(1, 2)
+    s = qf @ kf.transpose(-1, -2) * 0.125
+    if masked:
+        s = s + (1 - mask)[:, None, None, :] * -10000.0
+    ref = (torch.softmax(s, -1) @ vf).transpose(1, 2).reshape(B * Lq, E)
+    err = (out.float().cpu() - ref).abs().max().item()
+    assert err < 3e-2, err
+
+
+def c_off(t, elems):
+    import ctypes
+    return ctypes.c_void_p(t.data_ptr() + elems * t.element_size())

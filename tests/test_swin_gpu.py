@@ -1,0 +1,77 @@
+"""Swin-cls forward (C ABI) against the CPU oracle, stage by stage and at the logits (bf16 operands, fp32 accumulate,
+fp32 residual stream). Tolerances: north_star allows 1e-2 on logits in bf16 mode; block outputs are compared relative
+to their dynamic range."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+REL_TOL_BLOCK = 3e-2
+LOGIT_TOL = 1e-2
+
+
+@pytest.fixture(scope="module")
+def swin_pair():
+    from facialmmt_b200 import synthetic as syn
+    from facialmmt_b200.config import FmmtConfig
+    from facialmmt_b200.models import SwinForAffwildClassification
+    cfg = FmmtConfig()
+    sd = syn.swin_cls_stress_state_dict(cfg.swin, 1111)
+    m = SwinForAffwildClassification(cfg, swin_chunk=2, swin_chunk_late=3)   # exercise both chunk loops
+    m.load_state_dict(sd)
+    return cfg, sd, m
+
+
+def test_swin_stagewise_and_logits(swin_pair):
+    from facialmmt_b200 import synthetic as syn
+    from oracle import facialmmt_oracle as orc
+    cfg, sd, m = swin_pair
+    F = 5
+    frames = syn.synthetic_faces(F, 77)
+    col = {}
+    ref_logits = orc.swin_cls_logits(sd, frames, collect=col)
+    names = ["patch_embed"] + [f"layer{li}.block{bi}" for li, d in enumerate(cfg.swin.depths) for bi in range(d)]
+    caps = {n: m.capture("swin." + n, col[n].numel()) for n in names}
+    g = -torch.empty(F, 7).exponential_(generator=torch.Generator().manual_seed(1)).log()
+    logits, probs, imp, feat = m.forward_full(frames.cuda(), g, want_feat=True)
+    torch.cuda.synchronize()
+    m.clear_captures()
+    report = []
+    for n in names:
+        ref = col[n].reshape(-1)
+        got = caps[n].cpu()
+        assert torch.isfinite(got).all(), n
+        rel = (got - ref).abs().max().item() / ref.abs().max().item()
+        report.append((n, rel))
+    print("\nstage-wise max-abs error / max-abs value:", ", ".join(f"{n}={r:.2e}" for n, r in report))
+    for n, r in report:
+        assert r < REL_TOL_BLOCK, (n, r)
+    ref_feat = orc.swin_features(sd, frames)
+    ferr = (feat.cpu() - ref_feat).abs().max().item()
+    lerr = (logits.cpu() - ref_logits).abs().max().item()
+    print(f"feat512 max-abs err {ferr:.3e} (scale {ref_feat.abs().max():.2f}); logits max-abs err {lerr:.3e}")
+    assert lerr < LOGIT_TOL, lerr
+    assert torch.equal(logits.cpu().argmax(-1), ref_logits.argmax(-1))
+    ref_probs = orc.gumbel_softmax_probs(ref_logits, g, 1.0)
+    assert (probs.cpu() - ref_probs).abs().max().item() < LOGIT_TOL
+    assert (imp.cpu() - (ref_probs ** 2).sum(-1)).abs().max().item() < LOGIT_TOL
+
+
+def test_swin_batch_invariance_and_single_frame(swin_pair):
+    """Each frame's result must not depend on the batch/chunk composition (sharding relies on it); a lone frame
+    follows the duplicate-and-slice path of Swin_Transformer.py:535-538, a no-op in eval."""
+    from facialmmt_b200 import synthetic as syn
+    cfg, sd, m = swin_pair
+    frames = syn.synthetic_faces(7, 78).cuda()
+    full = m(frames, is_trg_task=False)
+    one = m(frames[3:4], is_trg_task=False)
+    part = m(frames[2:6], is_trg_task=False)
+    torch.cuda.synchronize()
+    assert torch.equal(full[3:4], one)
+    assert torch.equal(full[2:6], part)
+
+
+def test_swin_rejects_wrong_size(swin_pair):
+    cfg, sd, m = swin_pair
+    with pytest.raises(ValueError):
+        m(torch.zeros(1, 3, 112, 112), is_trg_task=False)
