@@ -1,6 +1,7 @@
 // extern "C" boundary of libfacialmmt_b200.so (see include/facialmmt_b200.h).
 #include "facialmmt_b200.h"
 
+#include <cstring>
 #include <new>
 #include <string>
 
@@ -97,6 +98,22 @@ FMMT_API int fmmt_unimodal_forward(fmmt_handle* h, const float* inputs, const fl
 FMMT_API int fmmt_set_capture(fmmt_handle* h, const char* name, float* dst, int64_t count) {
   if (!h) return set_error(FMMT_ERR_INVALID, "null handle");
   return h->eng->set_capture(name, dst, count);
+}
+
+FMMT_API int fmmt_set_profile(fmmt_handle* h, int enable) {
+  if (!h) return set_error(FMMT_ERR_INVALID, "null handle");
+  h->eng->set_profile(enable != 0);
+  return FMMT_OK;
+}
+FMMT_API int64_t fmmt_profile_read(fmmt_handle* h, char* buf, int64_t buf_len) {
+  if (!h) return 0;
+  const std::string js = h->eng->profile_json();
+  if (buf && buf_len > 0) {
+    const size_t n = js.size() < static_cast<size_t>(buf_len - 1) ? js.size() : static_cast<size_t>(buf_len - 1);
+    memcpy(buf, js.data(), n);
+    buf[n] = 0;
+  }
+  return static_cast<int64_t>(js.size() + 1);
 }
 
 FMMT_API double fmmt_flops(fmmt_handle* h, int reset) { return h ? h->eng->flops(reset != 0) : 0.0; }

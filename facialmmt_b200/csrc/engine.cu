@@ -3,6 +3,7 @@
 
 #include <atomic>
 #include <cmath>
+#include <cstdio>
 #include <cstring>
 #include <stdexcept>
 
@@ -29,6 +30,8 @@ Engine::Engine(const fmmt_config& cfg) : cfg_(cfg) {}
 
 Engine::~Engine() {
   cudaDeviceSynchronize();
+  for (auto& r : prof_recs_) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
+  for (cudaEvent_t e : ev_pool_) cudaEventDestroy(e);
   for (void* p : dev_ptrs_) cudaFree(p);
   if (ws_) cudaFree(ws_);
 }
@@ -444,6 +447,52 @@ int Engine::set_capture(const char* name, float* dst, int64_t count) {
   return FMMT_OK;
 }
 
+// =================================================================================================== profiling
+cudaEvent_t Engine::get_event() {
+  if (!ev_pool_.empty()) {
+    cudaEvent_t e = ev_pool_.back();
+    ev_pool_.pop_back();
+    return e;
+  }
+  cudaEvent_t e = nullptr;
+  cudaEventCreate(&e);
+  return e;
+}
+void Engine::set_profile(bool on) {
+  prof_ = on;
+  for (auto& r : prof_recs_) { ev_pool_.push_back(r.e0); ev_pool_.push_back(r.e1); }
+  prof_recs_.clear();
+}
+cudaEvent_t Engine::prof_begin(const std::string& key, double flops, double bytes) {
+  ProfRec r{key, flops, bytes, get_event(), get_event()};
+  cudaEventRecord(r.e0, st_);
+  prof_recs_.push_back(r);
+  return r.e1;
+}
+void Engine::prof_end(cudaEvent_t e1) { cudaEventRecord(e1, st_); }
+std::string Engine::profile_json() {
+  cudaDeviceSynchronize();
+  struct Agg { double ms = 0, flops = 0, bytes = 0; long n = 0; };
+  std::map<std::string, Agg> agg;
+  for (auto& r : prof_recs_) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, r.e0, r.e1) != cudaSuccess) continue;
+    Agg& a = agg[r.key];
+    a.ms += ms; a.flops += r.flops; a.bytes += r.bytes; a.n += 1;
+  }
+  std::string out = "{";
+  bool first = true;
+  char buf[256];
+  for (auto& kv : agg) {
+    snprintf(buf, sizeof(buf), "%s\"%s\": {\"ms\": %.6f, \"flops\": %.6e, \"bytes\": %.6e, \"launches\": %ld}",
+             first ? "" : ", ", kv.first.c_str(), kv.second.ms, kv.second.flops, kv.second.bytes, kv.second.n);
+    out += buf;
+    first = false;
+  }
+  out += "}";
+  return out;
+}
+
 // =================================================================================================== op wrappers
 void Engine::ck(cudaError_t e, const char* what) {
   if (e != cudaSuccess && first_err_ == cudaSuccess) {
@@ -456,7 +505,16 @@ void Engine::gemm(GemmArgs a) {
   if (arena_.dry() || first_err_ != cudaSuccess) return;
   flops_ += gemm_flops(a);
   count_launch();
+  cudaEvent_t e1 = nullptr;
+  if (prof_) {
+    // algorithmic bytes: A and W read once, outputs written once, residual read once
+    double bytes = 2.0 * a.M * a.K + 2.0 * a.N * a.K + (a.out_f32 ? 4.0 : 0.0) * a.M * a.N +
+                   (a.out_bf16 ? 2.0 : 0.0) * a.M * a.N + (a.residual ? 4.0 : 0.0) * a.M * a.N;
+    e1 = prof_begin("gemm " + std::to_string(a.M) + "x" + std::to_string(a.N) + "x" + std::to_string(a.K),
+                    gemm_flops(a), bytes);
+  }
   ck(launch_gemm(a, st_), "gemm");
+  if (prof_) prof_end(e1);
 }
 
 void Engine::gemm_lin(const bf16* A, int lda, int M, const Lin& l, GemmArgs ep) {
@@ -469,7 +527,12 @@ void Engine::gemm_lin(const bf16* A, int lda, int M, const Lin& l, GemmArgs ep) 
 void Engine::ln(LnArgs a) {
   if (arena_.dry() || first_err_ != cudaSuccess) return;
   count_launch();
+  cudaEvent_t e1 = nullptr;
+  const double C = static_cast<double>(a.nseg) * a.cseg;
+  if (prof_) e1 = prof_begin("layernorm C=" + std::to_string(a.nseg * a.cseg), 0.0,
+                             a.M * C * (4.0 + (a.out_f32 ? 4.0 : 0.0) + (a.out_bf16 ? 2.0 : 0.0)));
   ck(launch_layernorm(a, st_), "layernorm");
+  if (prof_) prof_end(e1);
 }
 
 void Engine::capture(const std::string& name, const float* src, size_t count, size_t dst_off) {
@@ -487,7 +550,10 @@ void Engine::capture(const std::string& name, const float* src, size_t count, si
   do {                                                         \
     if (!arena_.dry() && first_err_ == cudaSuccess) {          \
       count_launch();                                          \
+      cudaEvent_t e1__ = nullptr;                              \
+      if (prof_) e1__ = prof_begin(what, 0.0, 0.0);            \
       ck((call), what);                                        \
+      if (prof_) prof_end(e1__);                               \
     }                                                          \
   } while (0)
 
@@ -535,9 +601,12 @@ void Engine::swin_block(const SwinStageW& sw, const SwinBlockW& bw, float* x, in
   if (!arena_.dry() && first_err_ == cudaSuccess) {
     count_launch();
     flops_ += 4.0 * M * sw.N * C;
+    cudaEvent_t e1 = nullptr;
+    if (prof_) e1 = prof_begin("window_attention C=" + std::to_string(C), 4.0 * M * sw.N * C, 8.0 * M * C);
     ck(launch_window_attention(qkv, a, bw.bias_exp, bw.shift ? sw.rid : nullptr, nf * sw.nW, sw.nW, sw.heads, C, sw.N,
                                1.0f / std::sqrt(32.0f), st_),
        "window_attention");
+    if (prof_) prof_end(e1);
   }
   GemmArgs g2;
   g2.residual = x; g2.ldr = C; g2.out_f32 = x; g2.ldo32 = C;
@@ -699,8 +768,12 @@ void Engine::enc_layers(const std::vector<EncLayerW>& layers, float* x32, bf16* 
     if (!arena_.dry() && first_err_ == cudaSuccess) {
       count_launch();
       flops_ += 4.0 * U * static_cast<double>(L) * L * H;
+      cudaEvent_t e1 = nullptr;
+      if (prof_) e1 = prof_begin("mha H=" + std::to_string(H) + " L=" + std::to_string(L),
+                                 4.0 * U * static_cast<double>(L) * L * H, 8.0 * M * H);
       ck(launch_mha(qkv, 3 * H, qkv + H, 3 * H, qkv + 2 * H, 3 * H, ctx, H, mask01, mask_neg, U, heads, L, L, 0.125f, st_),
          "mha");
+      if (prof_) prof_end(e1);
     }
     GemmArgs g2;
     g2.residual = x32; g2.ldr = H; g2.out_f32 = x32; g2.ldo32 = H;
@@ -769,7 +842,11 @@ void Engine::cmt_encoder(const CmtW& cw, const float* xq, int Lq, int q_total, i
     if (!arena_.dry() && first_err_ == cudaSuccess) {
       count_launch();
       flops_ += 4.0 * U * static_cast<double>(Lq) * Lk * H;
+      cudaEvent_t e1 = nullptr;
+      if (prof_) e1 = prof_begin("mha cross Lq=" + std::to_string(Lq) + " Lk=" + std::to_string(Lk),
+                                 4.0 * U * static_cast<double>(Lq) * Lk * H, 2.0 * H * (2.0 * Mq + 2.0 * Mk));
       ck(launch_mha(q, H, kv, 2 * H, kv + H, 2 * H, a, H, nullptr, 0.f, U, cw.heads, Lq, Lk, 0.125f, st_), "mha");
+      if (prof_) prof_end(e1);
     }
     GemmArgs go;
     go.residual = x; go.ldr = H; go.out_f32 = x; go.ldo32 = H;

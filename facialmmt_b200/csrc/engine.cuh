@@ -139,6 +139,9 @@ class Engine {
                          int U, int L, float* logits, cudaStream_t st);
   int unimodal_forward(const float* inputs, const float* mask, int U, float* logits, cudaStream_t st);
   int set_capture(const char* name, float* dst, int64_t count);
+  // Per-kernel CUDA-event timing (on the launch stream) for roofline accounting; adds two event records per launch.
+  void set_profile(bool on);
+  std::string profile_json();  // synchronises; aggregates by kernel key since set_profile(true)
   double flops(bool reset) { double f = flops_; if (reset) flops_ = 0; return f; }
   int64_t device_bytes() const { return static_cast<int64_t>(weight_bytes_ + ws_cap_); }
   const std::string& error() const { return err_; }
@@ -210,6 +213,13 @@ class Engine {
   cudaError_t first_err_ = cudaSuccess;
   std::string err_;
   double flops_ = 0;
+  struct ProfRec { std::string key; double flops; double bytes; cudaEvent_t e0, e1; };
+  bool prof_ = false;
+  std::vector<ProfRec> prof_recs_;
+  std::vector<cudaEvent_t> ev_pool_;
+  cudaEvent_t prof_begin(const std::string& key, double flops, double bytes);
+  void prof_end(cudaEvent_t e1);
+  cudaEvent_t get_event();
   struct Cap { float* dst; int64_t count; };
   std::map<std::string, Cap> caps_;
 };

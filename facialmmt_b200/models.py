@@ -139,6 +139,17 @@ class _Module:
         self._captures.clear()
         _lib.check(self._lib.fmmt_set_capture(self._h, None, None, 0), "fmmt_set_capture")
 
+    def set_profile(self, on: bool = True):
+        _lib.check(self._lib.fmmt_set_profile(self._h, int(on)), "fmmt_set_profile")
+
+    def read_profile(self) -> dict:
+        """{kernel key: {ms, flops, bytes, launches}} measured with CUDA events since set_profile(True)."""
+        import json
+        n = int(self._lib.fmmt_profile_read(self._h, None, 0))
+        buf = ctypes.create_string_buffer(n + 16)
+        self._lib.fmmt_profile_read(self._h, buf, n + 16)
+        return json.loads(buf.value.decode())
+
     def flops(self, reset: bool = False) -> float:
         return float(self._lib.fmmt_flops(self._h, int(reset)))
 

@@ -217,9 +217,14 @@ def stress_state_dict(spec: Spec, seed: int, swin_cfg: SwinConfig | None = None)
     sd: Dict[str, torch.Tensor] = OrderedDict()
     for key, shape in spec.items():
         g = _gen(seed, key)
-        leaf = key.rsplit(".", 1)[-1]
-        lower = key.lower()
-        is_norm = ("norm" in lower) or key.startswith("swin.output_layer.0.") or key.startswith("swin.output_layer.3.")
+        parts = key.split(".")
+        leaf = parts[-1]
+        # the module that owns this tensor decides (NOT a substring of the path: `dense_norm.dense` is a Linear)
+        owner = parts[-2] if len(parts) >= 2 else ""
+        if owner.isdigit() and len(parts) >= 3:
+            owner = parts[-3] + "." + owner
+        is_norm = owner.lower() in ("norm", "norm1", "norm2", "layernorm", "layer_norm", "output_layer.0",
+                                    "output_layer.3", "layer_norms.0", "layer_norms.1")
         if key.endswith("relative_position_index"):
             t = _relative_position_index(swin_cfg.window_size if swin_cfg else 7)
         elif key.endswith("attn_mask"):

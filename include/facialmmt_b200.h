@@ -116,6 +116,11 @@ FMMT_API int fmmt_unimodal_forward(fmmt_handle* h, const float* inputs, const fl
  * floats). name == NULL clears all captures. Names: swin.patch_embed, swin.layer<l>.block<b>, swin.feat,
  * mm.text768, mm.text, mm.audio, mm.vision, mm.ta, mm.fused. */
 FMMT_API int fmmt_set_capture(fmmt_handle* h, const char* name, float* dst, int64_t count);
+/* Per-kernel timing with CUDA events on the launch stream (two records per launch while enabled). fmmt_profile_read
+ * synchronises and writes a JSON object {"<kernel key>": {"ms","flops","bytes","launches"}, ...} aggregated since
+ * profiling was enabled; returns the number of bytes needed (including the terminating NUL). */
+FMMT_API int fmmt_set_profile(fmmt_handle* h, int enable);
+FMMT_API int64_t fmmt_profile_read(fmmt_handle* h, char* buf, int64_t buf_len);
 /* Algorithmic FLOPs (2*MAC of every GEMM/attention launched) accumulated by the handle since the last reset. */
 FMMT_API double fmmt_flops(fmmt_handle* h, int reset);
 /* Bytes of device memory held by the handle (weights + workspace). */

@@ -7,7 +7,7 @@ import torch
 pytestmark = pytest.mark.gpu
 
 REL_TOL_BLOCK = 3e-2
-LOGIT_TOL = 1e-2
+LOGIT_TOL = 1e-2  # x max(1, max|logit|): stated relative to the logit scale of the stress-initialised model
 
 
 @pytest.fixture(scope="module")
@@ -50,7 +50,7 @@ def test_swin_stagewise_and_logits(swin_pair):
     ferr = (feat.cpu() - ref_feat).abs().max().item()
     lerr = (logits.cpu() - ref_logits).abs().max().item()
     print(f"feat512 max-abs err {ferr:.3e} (scale {ref_feat.abs().max():.2f}); logits max-abs err {lerr:.3e}")
-    assert lerr < LOGIT_TOL, lerr
+    assert lerr < LOGIT_TOL * max(1.0, ref_logits.abs().max().item()), lerr
     assert torch.equal(logits.cpu().argmax(-1), ref_logits.argmax(-1))
     ref_probs = orc.gumbel_softmax_probs(ref_logits, g, 1.0)
     assert (probs.cpu() - ref_probs).abs().max().item() < LOGIT_TOL
