@@ -32,10 +32,13 @@ __device__ __forceinline__ void mma_bf16(float (&d)[4], const uint32_t (&a)[4], 
 }
 
 // ------------------------------------------------------------------------------------------ Swin window attention
+// Persistent per head: a CTA keeps the relative-position bias of its head as MMA-fragment registers and streams
+// windows through a cp.async double buffer (q,k,v of one (window, head) = 3 x 49 x 64 B).
 constexpr int WA_D = 32;        // head_dim (all four Swin-tiny stages)
 constexpr int WA_PITCH = 40;    // smem row pitch in bf16 (80 B): conflict-free ldmatrix
 constexpr int WA_ROWS = 64;     // 49 tokens padded to 4 m-tiles
 constexpr int WA_NT = 7;        // key n-tiles (56 >= 49)
+constexpr float LOG2E = 1.4426950408889634f;
 
 struct WinAttnParams {
   const __nv_bfloat16* qkv;  // [num_windows*N, 3C], window order; q | k | v blocks of C, head h at h*32
@@ -46,129 +49,176 @@ struct WinAttnParams {
   float scale;
 };
 
-__global__ void __launch_bounds__(128) window_attention_kernel(const WinAttnParams p) {
-  __shared__ __align__(16) __nv_bfloat16 sQ[WA_ROWS * WA_PITCH];
-  __shared__ __align__(16) __nv_bfloat16 sK[WA_ROWS * WA_PITCH];
-  __shared__ __align__(16) __nv_bfloat16 sV[WA_ROWS * WA_PITCH];
-  __shared__ int8_t sRid[WA_ROWS];
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-  const int wb = blockIdx.x;   // window index over the whole batch
+__global__ void __launch_bounds__(128) window_attention_kernel(const WinAttnParams p) {
+  __shared__ __align__(16) __nv_bfloat16 sbuf[2][3][WA_ROWS * WA_PITCH];
+  __shared__ int8_t sRid[2][WA_ROWS];
+
   const int h = blockIdx.y;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int N = p.N;
   const int ld = 3 * p.C;
+  const bool use_mask = p.rid != nullptr;
 
-  // stage q, k, v (rows >= N zero-filled): 3 matrices x 64 rows x 4 chunks of 16 B
-  for (int idx = tid; idx < 3 * WA_ROWS * 4; idx += 128) {
-    const int mat = idx / (WA_ROWS * 4);
-    const int rem = idx - mat * (WA_ROWS * 4);
-    const int row = rem >> 2, ch = rem & 3;
-    uint4 v = make_uint4(0, 0, 0, 0);
-    if (row < N)
-      v = *reinterpret_cast<const uint4*>(p.qkv + (static_cast<size_t>(wb) * N + row) * ld + mat * p.C + h * WA_D +
-                                          ch * 8);
-    __nv_bfloat16* dst = (mat == 0 ? sQ : (mat == 1 ? sK : sV)) + row * WA_PITCH + ch * 8;
-    *reinterpret_cast<uint4*>(dst) = v;
+  // zero the padding rows (>= N) of both buffers once; they are never overwritten
+  for (int idx = tid; idx < 2 * 3 * WA_ROWS * 4; idx += 128) {
+    const int row = (idx >> 2) % WA_ROWS;
+    if (row >= N) {
+      const int bm = idx / (WA_ROWS * 4);
+      *reinterpret_cast<uint4*>(&sbuf[bm / 3][bm % 3][row * WA_PITCH + (idx & 3) * 8]) = make_uint4(0, 0, 0, 0);
+    }
   }
-  if (tid < WA_ROWS) sRid[tid] = (p.rid != nullptr && tid < N) ? p.rid[(wb % p.nW) * N + tid] : 0;
-  __syncthreads();
+  if (tid < 2 * WA_ROWS) sRid[tid / WA_ROWS][tid % WA_ROWS] = 0;
 
   const int r0 = warp * 16 + (lane >> 2);  // this thread's rows: r0 and r0 + 8
   const int cq = (lane & 3) * 2;
-
-  // S = Q K^T  (16 x 56 per warp)
-  float s[WA_NT][4];
+  // bias of this head in accumulator-fragment order, pre-multiplied by log2(e); key columns >= N -> -inf
+  float bfr[WA_NT][4];
+  {
+    const float* bias_h = p.bias + static_cast<size_t>(h) * N * N;
 #pragma unroll
-  for (int j = 0; j < WA_NT; ++j) s[j][0] = s[j][1] = s[j][2] = s[j][3] = 0.f;
+    for (int j = 0; j < WA_NT; ++j)
 #pragma unroll
-  for (int kk = 0; kk < WA_D / 16; ++kk) {
-    uint32_t a[4];
-    ldmatrix_x4(a, sQ + (warp * 16 + (lane & 15)) * WA_PITCH + kk * 16 + (lane >> 4) * 8);
-#pragma unroll
-    for (int jp = 0; jp < 4; ++jp) {  // key n-tile pairs (0,1) (2,3) (4,5) (6,7); tile 7 is discarded
-      uint32_t b[4];
-      ldmatrix_x4(b, sK + (jp * 16 + (lane & 7) + (lane >> 4) * 8) * WA_PITCH + kk * 16 + ((lane >> 3) & 1) * 8);
-      mma_bf16(s[2 * jp], a, b[0], b[1]);
-      if (2 * jp + 1 < WA_NT) mma_bf16(s[2 * jp + 1 < WA_NT ? 2 * jp + 1 : 0], a, b[2], b[3]);
-    }
-  }
-
-  // scale, + relative position bias, + shift mask; keys >= N excluded
-  const float* bias_h = p.bias + static_cast<size_t>(h) * N * N;
-  const bool use_mask = p.rid != nullptr;
-  float mx[2] = {-INFINITY, -INFINITY};
-#pragma unroll
-  for (int j = 0; j < WA_NT; ++j) {
-#pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      const int row = r0 + (e >> 1) * 8;
-      const int col = j * 8 + cq + (e & 1);
-      float v = -INFINITY;
-      if (col < N && row < N) {
-        v = s[j][e] * p.scale + __ldg(bias_h + row * N + col);
-        if (use_mask && sRid[row] != sRid[col]) v += -100.0f;
-      } else if (col < N) {
-        v = 0.f;  // padded query rows: keep finite, never stored
+      for (int e = 0; e < 4; ++e) {
+        const int row = r0 + (e >> 1) * 8, col = j * 8 + cq + (e & 1);
+        float v = -INFINITY;
+        if (col < N) v = row < N ? __ldg(bias_h + row * N + col) * LOG2E : 0.f;
+        bfr[j][e] = v;
       }
-      s[j][e] = v;
-      mx[e >> 1] = fmaxf(mx[e >> 1], v);
-    }
   }
-  float sum[2] = {0.f, 0.f};
-#pragma unroll
-  for (int hh = 0; hh < 2; ++hh) {
-    mx[hh] = fmaxf(mx[hh], __shfl_xor_sync(0xffffffffu, mx[hh], 1));
-    mx[hh] = fmaxf(mx[hh], __shfl_xor_sync(0xffffffffu, mx[hh], 2));
-  }
-#pragma unroll
-  for (int j = 0; j < WA_NT; ++j) {
-#pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      const float v = __expf(s[j][e] - mx[e >> 1]);
-      s[j][e] = v;
-      sum[e >> 1] += v;
-    }
-  }
-#pragma unroll
-  for (int hh = 0; hh < 2; ++hh) {
-    sum[hh] += __shfl_xor_sync(0xffffffffu, sum[hh], 1);
-    sum[hh] += __shfl_xor_sync(0xffffffffu, sum[hh], 2);
-  }
+  const float sscale = p.scale * LOG2E;
 
-  // O = P V  (16 x 32 per warp), P re-used from the S accumulators as bf16 A fragments
-  float o[4][4];
-#pragma unroll
-  for (int j = 0; j < 4; ++j) o[j][0] = o[j][1] = o[j][2] = o[j][3] = 0.f;
-#pragma unroll
-  for (int kk = 0; kk < 4; ++kk) {  // 16-key tiles; tile 3 = keys 48..63 (n-tile 6 + zeros)
-    uint32_t a[4];
-    a[0] = pack_bf16(s[2 * kk][0], s[2 * kk][1]);
-    a[1] = pack_bf16(s[2 * kk][2], s[2 * kk][3]);
-    if (2 * kk + 1 < WA_NT) {
-      a[2] = pack_bf16(s[(2 * kk + 1) % WA_NT][0], s[(2 * kk + 1) % WA_NT][1]);
-      a[3] = pack_bf16(s[(2 * kk + 1) % WA_NT][2], s[(2 * kk + 1) % WA_NT][3]);
+  auto issue = [&](int wb, int b) {
+    // 3 matrices x N rows x 4 chunks of 16 B
+    for (int idx = tid; idx < 3 * N * 4; idx += 128) {
+      const int mat = idx / (N * 4);
+      const int rem = idx - mat * (N * 4);
+      const int row = rem >> 2, ch = rem & 3;
+      cp_async16(&sbuf[b][mat][row * WA_PITCH + ch * 8],
+                 p.qkv + (static_cast<size_t>(wb) * N + row) * ld + mat * p.C + h * WA_D + ch * 8);
+    }
+    cp_async_commit();
+  };
+
+  int wb = blockIdx.x;
+  int b = 0;
+  if (wb < p.num_windows) issue(wb, 0);
+  for (; wb < p.num_windows; wb += gridDim.x, b ^= 1) {
+    const int nxt = wb + gridDim.x;
+    if (nxt < p.num_windows) {
+      issue(nxt, b ^ 1);
+      cp_async_wait<1>();
     } else {
-      a[2] = 0u;
-      a[3] = 0u;
+      cp_async_wait<0>();
+    }
+    if (use_mask && tid < N) sRid[b][tid] = p.rid[(wb % p.nW) * N + tid];
+    __syncthreads();
+    const __nv_bfloat16* sQ = sbuf[b][0];
+    const __nv_bfloat16* sK = sbuf[b][1];
+    const __nv_bfloat16* sV = sbuf[b][2];
+
+    // S = Q K^T  (16 x 56 per warp)
+    float s[WA_NT][4];
+#pragma unroll
+    for (int j = 0; j < WA_NT; ++j) s[j][0] = s[j][1] = s[j][2] = s[j][3] = 0.f;
+#pragma unroll
+    for (int kk = 0; kk < WA_D / 16; ++kk) {
+      uint32_t a[4];
+      ldmatrix_x4(a, sQ + (warp * 16 + (lane & 15)) * WA_PITCH + kk * 16 + (lane >> 4) * 8);
+#pragma unroll
+      for (int jp = 0; jp < 4; ++jp) {  // key n-tile pairs (0,1) (2,3) (4,5) (6,-)
+        uint32_t bb[4];
+        ldmatrix_x4(bb, sK + (jp * 16 + (lane & 7) + (lane >> 4) * 8) * WA_PITCH + kk * 16 + ((lane >> 3) & 1) * 8);
+        mma_bf16(s[2 * jp], a, bb[0], bb[1]);
+        if (jp < 3) mma_bf16(s[jp < 3 ? 2 * jp + 1 : 0], a, bb[2], bb[3]);
+      }
+    }
+    // log2-domain logits: s*scale*log2e + bias*log2e (+ mask); row max; exp2
+    float mx[2] = {-INFINITY, -INFINITY};
+    if (use_mask) {
+      const int8_t rr0 = sRid[b][r0], rr1 = sRid[b][(r0 + 8) & 63];
+#pragma unroll
+      for (int j = 0; j < WA_NT; ++j) {
+        const int8_t c0 = sRid[b][j * 8 + cq], c1 = sRid[b][j * 8 + cq + 1];
+        s[j][0] = fmaf(s[j][0], sscale, bfr[j][0]) + (rr0 != c0 ? -100.f * LOG2E : 0.f);
+        s[j][1] = fmaf(s[j][1], sscale, bfr[j][1]) + (rr0 != c1 ? -100.f * LOG2E : 0.f);
+        s[j][2] = fmaf(s[j][2], sscale, bfr[j][2]) + (rr1 != c0 ? -100.f * LOG2E : 0.f);
+        s[j][3] = fmaf(s[j][3], sscale, bfr[j][3]) + (rr1 != c1 ? -100.f * LOG2E : 0.f);
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < WA_NT; ++j)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) s[j][e] = fmaf(s[j][e], sscale, bfr[j][e]);
     }
 #pragma unroll
-    for (int np = 0; np < 2; ++np) {  // dim n-tile pairs (0,1), (2,3)
-      uint32_t b[4];
-      ldmatrix_x4_trans(b, sV + (kk * 16 + (lane & 7) + ((lane >> 3) & 1) * 8) * WA_PITCH + np * 16 + (lane >> 4) * 8);
-      mma_bf16(o[2 * np], a, b[0], b[1]);
-      mma_bf16(o[2 * np + 1], a, b[2], b[3]);
+    for (int j = 0; j < WA_NT; ++j) {
+      mx[0] = fmaxf(mx[0], fmaxf(s[j][0], s[j][1]));
+      mx[1] = fmaxf(mx[1], fmaxf(s[j][2], s[j][3]));
     }
-  }
-  const float inv0 = 1.f / sum[0], inv1 = 1.f / sum[1];
+    float sum[2] = {0.f, 0.f};
 #pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    const int col = h * WA_D + j * 8 + cq;
-    if (r0 < N)
-      *reinterpret_cast<uint32_t*>(p.out + (static_cast<size_t>(wb) * N + r0) * p.C + col) =
-          pack_bf16(o[j][0] * inv0, o[j][1] * inv0);
-    if (r0 + 8 < N)
-      *reinterpret_cast<uint32_t*>(p.out + (static_cast<size_t>(wb) * N + r0 + 8) * p.C + col) =
-          pack_bf16(o[j][2] * inv1, o[j][3] * inv1);
+    for (int hh = 0; hh < 2; ++hh) {
+      mx[hh] = fmaxf(mx[hh], __shfl_xor_sync(0xffffffffu, mx[hh], 1));
+      mx[hh] = fmaxf(mx[hh], __shfl_xor_sync(0xffffffffu, mx[hh], 2));
+    }
+#pragma unroll
+    for (int j = 0; j < WA_NT; ++j) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float v = exp2f(s[j][e] - mx[e >> 1]);
+        s[j][e] = v;
+        sum[e >> 1] += v;
+      }
+    }
+#pragma unroll
+    for (int hh = 0; hh < 2; ++hh) {
+      sum[hh] += __shfl_xor_sync(0xffffffffu, sum[hh], 1);
+      sum[hh] += __shfl_xor_sync(0xffffffffu, sum[hh], 2);
+    }
+
+    // O = P V  (16 x 32 per warp), P re-used from the S accumulators as bf16 A fragments
+    float o[4][4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) o[j][0] = o[j][1] = o[j][2] = o[j][3] = 0.f;
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) {  // 16-key tiles; tile 3 = keys 48..63 (n-tile 6 + zeros)
+      uint32_t a[4];
+      a[0] = pack_bf16(s[2 * kk][0], s[2 * kk][1]);
+      a[1] = pack_bf16(s[2 * kk][2], s[2 * kk][3]);
+      if (kk < 3) {
+        a[2] = pack_bf16(s[kk < 3 ? 2 * kk + 1 : 0][0], s[kk < 3 ? 2 * kk + 1 : 0][1]);
+        a[3] = pack_bf16(s[kk < 3 ? 2 * kk + 1 : 0][2], s[kk < 3 ? 2 * kk + 1 : 0][3]);
+      } else {
+        a[2] = 0u;
+        a[3] = 0u;
+      }
+#pragma unroll
+      for (int np = 0; np < 2; ++np) {  // dim n-tile pairs (0,1), (2,3)
+        uint32_t bb[4];
+        ldmatrix_x4_trans(bb, sV + (kk * 16 + (lane & 7) + ((lane >> 3) & 1) * 8) * WA_PITCH + np * 16 + (lane >> 4) * 8);
+        mma_bf16(o[2 * np], a, bb[0], bb[1]);
+        mma_bf16(o[2 * np + 1], a, bb[2], bb[3]);
+      }
+    }
+    const float inv0 = 1.f / sum[0], inv1 = 1.f / sum[1];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int col = h * WA_D + j * 8 + cq;
+      if (r0 < N)
+        *reinterpret_cast<uint32_t*>(p.out + (static_cast<size_t>(wb) * N + r0) * p.C + col) =
+            pack_bf16(o[j][0] * inv0, o[j][1] * inv0);
+      if (r0 + 8 < N)
+        *reinterpret_cast<uint32_t*>(p.out + (static_cast<size_t>(wb) * N + r0 + 8) * p.C + col) =
+            pack_bf16(o[j][2] * inv1, o[j][3] * inv1);
+    }
+    __syncthreads();  // every warp is done with buffer b before the next iteration refills it
   }
 }
 
@@ -329,7 +379,10 @@ cudaError_t launch_window_attention(const __nv_bfloat16* qkv, __nv_bfloat16* out
                                     cudaStream_t stream) {
   if (C != heads * WA_D || N > 49 || N < 1 || num_windows <= 0 || (C % 8) != 0) return cudaErrorInvalidValue;
   WinAttnParams p{qkv, out, bias, rid, num_windows, nW, heads, C, N, scale};
-  dim3 grid(num_windows, heads);
+  // persistent over windows: ~6 resident CTAs per SM in total, split across the heads (grid.y)
+  int gx = (148 * 6 + heads - 1) / heads;
+  if (gx > num_windows) gx = num_windows;
+  dim3 grid(gx, heads);
   window_attention_kernel<<<grid, 128, 0, stream>>>(p);
   return cudaGetLastError();
 }

@@ -133,7 +133,8 @@ FMMT_API int fmmt_op_gemm(const void* A_bf16, int lda, const void* W_bf16, int l
   a.out_f32 = out_f32; a.ldo32 = ldo32;
   a.out_bf16 = static_cast<__nv_bfloat16*>(out_bf16); a.ldo16 = ldo16;
   a.row_map = row_map; a.map_period = map_period;
-  a.block_n = block_n;
+  a.block_n = block_n < 0 ? (block_n == -1 ? 0 : -block_n) : block_n;
+  a.force_generic = block_n < 0;
   count_launch();
   return check_cuda(launch_gemm(a, S(stream)), "fmmt_op_gemm");
 }

@@ -147,23 +147,24 @@ void Engine::pack_swin() {
     sw.nW = nw * nw;
     const int T = R * R;
     const int s = c.window_size / 2;
+    // window-order row (wy,wx,ty,tx) reads token ((wy*ws+ty+shift)%R, (wx*ws+tx+shift)%R): torch.roll(-shift) then
+    // window_partition (Swin_Transformer.py:244,43-44); window_reverse + roll(+shift) is its inverse (:258-264).
+    std::vector<int> pi[2];
     for (int v = 0; v < 2; ++v) {
       const int shift = v == 0 ? 0 : (shiftable ? s : 0);
-      std::vector<int> map(T);
-      // window-order row (wy,wx,ty,tx) reads token ((wy*ws+ty+shift)%R, (wx*ws+tx+shift)%R): torch.roll(-shift) then
-      // window_partition (Swin_Transformer.py:244,43-44); the same map scatters back (window_reverse + roll(+shift)).
+      pi[v].resize(T);
       int r = 0;
       for (int wy = 0; wy < nw; ++wy)
         for (int wx = 0; wx < nw; ++wx)
           for (int ty = 0; ty < sw.ws; ++ty)
             for (int tx = 0; tx < sw.ws; ++tx) {
               const int hh = (wy * sw.ws + ty + shift) % R, ww = (wx * sw.ws + tx + shift) % R;
-              map[r++] = hh * R + ww;
+              pi[v][r++] = hh * R + ww;
             }
-      int* d = dev_alloc<int>(T);
-      cudaMemcpy(d, map.data(), T * sizeof(int), cudaMemcpyHostToDevice);
-      sw.win_map[v] = d;
     }
+    // sigma_inv[t] = row of the residual stream that currently holds natural token t (identity at stage entry)
+    std::vector<int> sigma_inv(T);
+    for (int t = 0; t < T; ++t) sigma_inv[t] = t;
     if (shiftable) {
       // region ids in shifted coordinates (Swin_Transformer.py:208-229): mask[i][j] = rid_i != rid_j ? -100 : 0
       std::vector<int8_t> rid(static_cast<size_t>(sw.nW) * sw.N);
@@ -181,6 +182,22 @@ void Engine::pack_swin() {
       const std::string p = "swin.layers." + std::to_string(li) + ".blocks." + std::to_string(bi) + ".";
       SwinBlockW bw;
       bw.shift = (bi % 2 == 1 && shiftable) ? s : 0;
+      {
+        const std::vector<int>& p_b = pi[bw.shift ? 1 : 0];
+        std::vector<int> g(T), inv(T);
+        bool ident = true;
+        for (int r = 0; r < T; ++r) {
+          g[r] = sigma_inv[p_b[r]];      // row r of this block's window order <- current row of token p_b[r]
+          ident = ident && g[r] == r;
+        }
+        for (int r = 0; r < T; ++r) inv[p_b[r]] = r;   // after the block, token p_b[r] lives at row r
+        sigma_inv = inv;
+        bw.identity = ident;
+        bw.gather = dev_alloc<int>(T);
+        cudaMemcpy(bw.gather, g.data(), T * sizeof(int), cudaMemcpyHostToDevice);
+        bw.to_natural = dev_alloc<int>(T);
+        cudaMemcpy(bw.to_natural, inv.data(), T * sizeof(int), cudaMemcpyHostToDevice);
+      }
       bw.ln1 = norm(p + "norm1.");
       bw.ln2 = norm(p + "norm2.");
       bw.qkv = lin(p + "attn.qkv.");
@@ -215,13 +232,24 @@ void Engine::pack_swin() {
       for (int y = 0; y < R2; ++y)
         for (int x = 0; x < R2; ++x) {
           int* q = &mm[(static_cast<size_t>(y) * R2 + x) * 4];
-          q[0] = (2 * y) * R + 2 * x;          // x0 = x[0::2, 0::2]   (Swin_Transformer.py:318-322)
-          q[1] = (2 * y + 1) * R + 2 * x;      // x1 = x[1::2, 0::2]
-          q[2] = (2 * y) * R + 2 * x + 1;      // x2 = x[0::2, 1::2]
-          q[3] = (2 * y + 1) * R + 2 * x + 1;  // x3 = x[1::2, 1::2]
+          // tokens x0 = x[0::2,0::2], x1 = x[1::2,0::2], x2 = x[0::2,1::2], x3 = x[1::2,1::2]
+          // (Swin_Transformer.py:318-322), looked up in the stream order left by the stage's last block
+          q[0] = sigma_inv[(2 * y) * R + 2 * x];
+          q[1] = sigma_inv[(2 * y + 1) * R + 2 * x];
+          q[2] = sigma_inv[(2 * y) * R + 2 * x + 1];
+          q[3] = sigma_inv[(2 * y + 1) * R + 2 * x + 1];
         }
       sw.merge_map = dev_alloc<int>(mm.size());
       cudaMemcpy(sw.merge_map, mm.data(), mm.size() * sizeof(int), cudaMemcpyHostToDevice);
+    }
+    if (li == c.num_stages - 1) {
+      // the head flattens tokens in natural order (Swin_Transformer.py:492): keep a final un-permute map if needed
+      bool ident = true;
+      for (int t = 0; t < T; ++t) ident = ident && sigma_inv[t] == t;
+      if (!ident) {
+        swin_.final_gather = dev_alloc<int>(T);
+        cudaMemcpy(swin_.final_gather, sigma_inv.data(), T * sizeof(int), cudaMemcpyHostToDevice);
+      }
     }
     swin_.stages.push_back(sw);
     if (li < c.num_stages - 1) { R /= 2; C *= 2; }
@@ -585,16 +613,32 @@ int Engine::run(Fn&& body, cudaStream_t st) {
 }
 
 // =================================================================================================== Swin forward
-void Engine::swin_block(const SwinStageW& sw, const SwinBlockW& bw, float* x, int nf, bf16* h, bf16* qkv, bf16* a,
-                        bf16* hid) {
+void Engine::capture_block(const std::string& name, const SwinStageW& sw, const SwinBlockW& bw, const float* x, int nf,
+                           int f0) {
+  if (arena_.dry() || first_err_ != cudaSuccess || caps_.empty()) return;
+  auto it = caps_.find(name);
+  if (it == caps_.end()) return;
+  const int T = sw.R * sw.R;
+  const size_t off = static_cast<size_t>(f0) * T * sw.C, count = static_cast<size_t>(nf) * T * sw.C;
+  if (off + count > static_cast<size_t>(it->second.count)) return;
+  // the stream is in this block's window order: un-permute into natural token order for the parity tests
+  ck(launch_gather_rows(x, bw.to_natural, T, sw.C, nf * T, it->second.dst + off, st_), "capture gather");
+}
+
+void Engine::swin_block(const SwinStageW& sw, const SwinBlockW& bw, float*& x, float*& xalt, int nf, bf16* h, bf16* qkv,
+                        bf16* a, bf16* hid) {
   const int T = sw.R * sw.R, C = sw.C, M = nf * T;
-  const int* map = sw.win_map[bw.shift ? 1 : 0];
   LnArgs l1;
   l1.in = x; l1.ld_in = C; l1.M = M; l1.nseg = 1; l1.cseg = C;
-  l1.map = map; l1.map_period = T; l1.src_period = T;
   l1.gamma = bw.ln1.g; l1.beta = bw.ln1.b; l1.eps = 1e-5f;
   l1.out_bf16 = h; l1.ld16 = C;
-  ln(l1);                                                           // norm1 + roll + window_partition
+  if (!bw.identity) {
+    // norm1 + roll + window_partition as ONE row gather; the gathered raw rows become the new residual stream
+    l1.map = bw.gather; l1.map_period = T; l1.src_period = T;
+    l1.out_raw = xalt; l1.ld_raw = C;
+  }
+  ln(l1);
+  if (!bw.identity) std::swap(x, xalt);
   GemmArgs g1;
   g1.out_bf16 = qkv; g1.ldo16 = 3 * C;
   gemm_lin(h, C, M, bw.qkv, g1);                                    // qkv Linear
@@ -608,10 +652,9 @@ void Engine::swin_block(const SwinStageW& sw, const SwinBlockW& bw, float* x, in
        "window_attention");
     if (prof_) prof_end(e1);
   }
-  GemmArgs g2;
+  GemmArgs g2;                                                      // proj + shortcut, in window order (no scatter)
   g2.residual = x; g2.ldr = C; g2.out_f32 = x; g2.ldo32 = C;
-  g2.row_map = map; g2.map_period = T;
-  gemm_lin(a, C, M, bw.proj, g2);                                   // proj + window_reverse + roll back + shortcut
+  gemm_lin(a, C, M, bw.proj, g2);
   LnArgs l2;
   l2.in = x; l2.ld_in = C; l2.M = M; l2.cseg = C;
   l2.gamma = bw.ln2.g; l2.beta = bw.ln2.b; l2.eps = 1e-5f;
@@ -635,6 +678,7 @@ void Engine::swin_early(const float* frames, int f0, int nf, float* x_out) {
   int M = nf * T0;
   bf16* col = arena_.alloc<bf16>(static_cast<size_t>(M) * 48);
   float* x = (split == 0) ? x_out : arena_.alloc<float>(static_cast<size_t>(M) * C0);
+  float* xalt = (split == 0) ? nullptr : arena_.alloc<float>(static_cast<size_t>(M) * C0);
   bf16* h = arena_.alloc<bf16>(static_cast<size_t>(M) * C0);
   bf16* qkv = arena_.alloc<bf16>(static_cast<size_t>(M) * 3 * C0);
   bf16* a = arena_.alloc<bf16>(static_cast<size_t>(M) * C0);
@@ -654,9 +698,8 @@ void Engine::swin_early(const float* frames, int f0, int nf, float* x_out) {
     const SwinStageW& sw = swin_.stages[li];
     const int T = sw.R * sw.R;
     for (size_t bi = 0; bi < sw.blocks.size(); ++bi) {
-      swin_block(sw, sw.blocks[bi], x, nf, h, qkv, a, hid);
-      capture("swin.layer" + std::to_string(li) + ".block" + std::to_string(bi), x, static_cast<size_t>(nf) * T * sw.C,
-              static_cast<size_t>(f0) * T * sw.C);
+      swin_block(sw, sw.blocks[bi], x, xalt, nf, h, qkv, a, hid);
+      capture_block("swin.layer" + std::to_string(li) + ".block" + std::to_string(bi), sw, sw.blocks[bi], x, nf, f0);
     }
     LnArgs lm;                                                       // PatchMerging: gather 2x2 -> LN(4C) -> Linear
     lm.in = x; lm.ld_in = sw.C; lm.M = nf * T / 4; lm.nseg = 4; lm.cseg = sw.C;
@@ -676,6 +719,7 @@ void Engine::swin_late(float* x, int f0, int nf, bf16* feat_ln) {
   const int split = swin_split(c);
   const SwinStageW& s0 = swin_.stages[split];
   const size_t M0 = static_cast<size_t>(nf) * s0.R * s0.R;
+  float* xalt = arena_.alloc<float>(M0 * s0.C);
   bf16* h = arena_.alloc<bf16>(M0 * s0.C);
   bf16* qkv = arena_.alloc<bf16>(M0 * 3 * s0.C);
   bf16* a = arena_.alloc<bf16>(M0 * s0.C);
@@ -684,9 +728,8 @@ void Engine::swin_late(float* x, int f0, int nf, bf16* feat_ln) {
     const SwinStageW& sw = swin_.stages[li];
     const int T = sw.R * sw.R;
     for (size_t bi = 0; bi < sw.blocks.size(); ++bi) {
-      swin_block(sw, sw.blocks[bi], x, nf, h, qkv, a, hid);
-      capture("swin.layer" + std::to_string(li) + ".block" + std::to_string(bi), x, static_cast<size_t>(nf) * T * sw.C,
-              static_cast<size_t>(f0) * T * sw.C);
+      swin_block(sw, sw.blocks[bi], x, xalt, nf, h, qkv, a, hid);
+      capture_block("swin.layer" + std::to_string(li) + ".block" + std::to_string(bi), sw, sw.blocks[bi], x, nf, f0);
     }
     if (sw.has_merge) {
       LnArgs lm;
@@ -704,6 +747,7 @@ void Engine::swin_late(float* x, int f0, int nf, bf16* feat_ln) {
   const int Tl = sl.R * sl.R;
   LnArgs lf;                                                         // output_layer[0]: LayerNorm, token-major flatten
   lf.in = x; lf.ld_in = sl.C; lf.M = nf * Tl; lf.cseg = sl.C;
+  if (swin_.final_gather != nullptr) { lf.map = swin_.final_gather; lf.map_period = Tl; lf.src_period = Tl; }
   lf.gamma = swin_.head_ln.g; lf.beta = swin_.head_ln.b; lf.eps = 1e-5f;
   lf.out_bf16 = feat_ln + static_cast<size_t>(f0) * Tl * sl.C; lf.ld16 = sl.C;
   ln(lf);

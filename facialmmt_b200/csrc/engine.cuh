@@ -44,14 +44,18 @@ struct SwinBlockW {
   Lin qkv, proj, fc1, fc2;
   float* bias_exp = nullptr;  // [heads, N, N]
   int shift = 0;
+  // The residual stream is kept in the window order of the most recent attention block, so that every GEMM output
+  // is written in place order (TMA-storable) and the only permutations are row gathers inside LayerNorm:
+  int* gather = nullptr;      // [T] window-order row r of THIS block <- row gather[r] of the current stream order
+  int* to_natural = nullptr;  // [T] natural token t sits at row to_natural[t] after this block (parity captures)
+  bool identity = false;      // gather is the identity (stage with a single window): no copy needed
 };
 struct SwinStageW {
   int R = 0, C = 0, heads = 0, ws = 0, N = 0, nW = 0;
-  int* win_map[2] = {nullptr, nullptr};  // [T] window-order row -> token, for shift 0 and shift ws/2
   int8_t* rid = nullptr;                 // [nW, N] region ids for shifted blocks
   std::vector<SwinBlockW> blocks;
   bool has_merge = false;
-  int* merge_map = nullptr;  // [T/4, 4]
+  int* merge_map = nullptr;  // [T/4, 4] rows of the current stream order (after the stage's last block)
   Norm merge_ln;
   Lin merge;
 };
@@ -60,6 +64,7 @@ struct SwinW {
   Norm patch_ln;
   std::vector<SwinStageW> stages;
   Norm head_ln;
+  int* final_gather = nullptr;  // natural token -> stream row after the last block (nullptr: already natural)
   Lin head;  // [feat, R*R*C] with BatchNorm folded in
   float* w1t = nullptr;  // [feat, hidden]
   float* b1 = nullptr;
@@ -179,7 +184,9 @@ class Engine {
                  float* importance, float* feat);
   void swin_early(const float* frames, int f0, int nf, float* x2_out);
   void swin_late(float* x2, int f0, int nf, bf16* feat_ln);
-  void swin_block(const SwinStageW& sw, const SwinBlockW& bw, float* x, int nf, bf16* h, bf16* qkv, bf16* a, bf16* hid);
+  void swin_block(const SwinStageW& sw, const SwinBlockW& bw, float*& x, float*& xalt, int nf, bf16* h, bf16* qkv,
+                  bf16* a, bf16* hid);
+  void capture_block(const std::string& name, const SwinStageW& sw, const SwinBlockW& bw, const float* x, int nf, int f0);
   void enc_layers(const std::vector<EncLayerW>& layers, float* x32, bf16* x16, int U, int L, int H, int heads, int ffn,
                   const float* mask01, float mask_neg, float eps);
   void meld_encoder(const MeldEncW& m, const float* in, int in_dim, int U, int L, const float* mask01, float* x32,

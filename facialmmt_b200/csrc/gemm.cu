@@ -1,7 +1,8 @@
 // Persistent, warp-specialised bf16 GEMM for sm_100a:
 //   TMA (cp.async.bulk.tensor, SWIZZLE_128B) -> shared-memory ring -> tcgen05.mma (fp32 accumulators in TMEM,
 //   double-buffered) -> tcgen05.ld epilogue with fused bias / GELU(erf) / tanh / residual / row scatter.
-// One CTA per SM; warps 0-3 = epilogue (TMEM lane quarters), warp 4 = TMA producer, warp 5 = MMA issuer + TMEM owner.
+// One CTA per SM; warps 0-7 = epilogue (two per TMEM lane quarter, smem-transposed coalesced stores), warp 8 = TMA
+// producer, warp 9 = MMA issuer + TMEM owner.
 //
 // Replaces every nn.Linear on the reference path (e.g. Swin_Transformer.py:24-30,119,142,325; Transformer.py:87-89,
 // 132,145,159; multihead_attention.py:151-158; CrossmodalTransformer.py:157-160; src/models.py:107,158,165).
@@ -17,7 +18,12 @@ namespace {
 constexpr int BM = 128;
 constexpr int BK = 64;  // 64 bf16 = one 128-byte swizzle row
 constexpr int UMMA_K = 16;
-constexpr int GEMM_THREADS = 192;
+constexpr int EPI_WARPS = 8;          // 2 per TMEM lane quarter
+constexpr int PRODUCER_WARP = 8;
+constexpr int MMA_WARP = 9;
+constexpr int GEMM_THREADS = 320;
+constexpr int EPI_PITCH = 36;         // floats per staged row (32 + 4 pad): conflict-free v4 writes and row reads
+constexpr int EPI_STAGING_BYTES = ((EPI_WARPS * 32 * EPI_PITCH * 4 + 1023) / 1024) * 1024;
 constexpr int MAX_STAGES = 8;
 constexpr int TMEM_COLS = 512;       // two accumulator stages of up to 256 fp32 columns
 constexpr int ACC_STRIDE = 256;
@@ -63,9 +69,12 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  // SWIZZLE_128B tiles need 1024-byte alignment.
+  // SWIZZLE_128B tiles need 1024-byte alignment. Layout: [epilogue staging | pipeline stages]
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  float* stage_f32 = reinterpret_cast<float*>(smem_gen);            // EPI_WARPS x [32][EPI_PITCH] floats
+  uint8_t* pipe_gen = smem_gen + EPI_STAGING_BYTES;
+  const uint32_t pipe_base = smem_base + EPI_STAGING_BYTES;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.num_stages; ++s) {
@@ -74,15 +83,15 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tmem_full_bar[s], 1);
-      mbar_init(&tmem_empty_bar[s], 128);
+      mbar_init(&tmem_empty_bar[s], EPI_WARPS * 32);
     }
     fence_barrier_init();
   }
-  if (warp == 4 && lane == 0) {
+  if (warp == PRODUCER_WARP && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
   }
-  if (warp == 5) {
+  if (warp == MMA_WARP) {
     tmem_alloc(&tmem_base_slot, TMEM_COLS);
     tmem_relinquish();
   }
@@ -93,7 +102,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
 
   const int num_tiles = p.m_tiles * p.n_tiles;
 
-  if (warp == 4) {
+  if (warp == PRODUCER_WARP) {
     // ------------------------------------------------------------ TMA producer
     if (lane == 0) {
       int stage = 0;
@@ -103,7 +112,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
         const int n0 = (tile % p.n_tiles) * p.block_n;
         for (int kb = 0; kb < p.num_kb; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1u);
-          uint8_t* sa = smem_gen + stage * p.stage_bytes;
+          uint8_t* sa = pipe_gen + stage * p.stage_bytes;
           uint8_t* sb = sa + A_TILE_BYTES;
           mbar_arrive_expect_tx(&full_bar[stage], static_cast<uint32_t>(p.stage_bytes));
           tma_load_2d(sa, &tmA, &full_bar[stage], kb * BK, m0);
@@ -112,7 +121,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
         }
       }
     }
-  } else if (warp == 5) {
+  } else if (warp == MMA_WARP) {
     // ------------------------------------------------------------ MMA issuer (one thread)
     if (lane == 0) {
       const uint32_t idesc = make_idesc_bf16(BM, p.block_n);
@@ -127,7 +136,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
         for (int kb = 0; kb < p.num_kb; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
-          const uint32_t sa = smem_base + stage * p.stage_bytes;
+          const uint32_t sa = pipe_base + stage * p.stage_bytes;
           const uint64_t adesc = make_smem_desc_sw128(sa);
           const uint64_t bdesc = make_smem_desc_sw128(sa + A_TILE_BYTES);
           int ksteps = (p.K - kb * BK + UMMA_K - 1) / UMMA_K;
@@ -146,83 +155,99 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
       }
     }
   } else {
-    // ------------------------------------------------------------ epilogue warps 0..3 (TMEM lanes 32*warp..)
+    // ------------------------------------------------------------ epilogue warps 0..7
+    // Warp w owns TMEM lanes 32*(w%4).. (hardware restriction) and the 32-column chunks with parity w/4.
+    // Each chunk: tcgen05.ld (thread = row) -> per-warp smem transpose -> lanes (8 per row, float4 each) apply
+    // bias / activation / residual and store 128-byte row segments: fully coalesced global traffic.
+    const int quarter = warp & 3;
+    const int parity = warp >> 2;
+    float* st = stage_f32 + warp * (32 * EPI_PITCH);
+    const int sub = lane >> 3;   // row within a group of 4
+    const int c4 = lane & 7;     // float4 column within the 32-column chunk
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int m0 = (tile / p.n_tiles) * BM;
       const int n0 = (tile % p.n_tiles) * p.block_n;
+      // destination rows of the 8 rows this lane stores: local row 4*i + sub
+      long long drow[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int row = m0 + quarter * 32 + 4 * i + sub;
+        long long dest = -1;
+        if (row < p.M) {
+          dest = row;
+          if (p.row_map != nullptr) {
+            const int q = row / p.map_period;
+            dest = static_cast<long long>(q) * p.map_period + __ldg(p.row_map + (row - q * p.map_period));
+          }
+          if (p.rows_in > 0) {
+            const long long q = dest / p.rows_in;
+            dest = q * p.rows_out + p.row_off + (dest - q * p.rows_in);
+          }
+        }
+        drow[i] = dest;
+      }
       mbar_wait(&tmem_full_bar[acc], acc_phase);
       tc_fence_after();
-      const int row = m0 + warp * 32 + lane;
-      const bool row_ok = row < p.M;
-      long long dest = row;
-      if (row_ok) {
-        if (p.row_map != nullptr) {
-          const int q = row / p.map_period;
-          dest = static_cast<long long>(q) * p.map_period + p.row_map[row - q * p.map_period];
-        }
-        if (p.rows_in > 0) {
-          const long long q = dest / p.rows_in;
-          dest = q * p.rows_out + p.row_off + (dest - q * p.rows_in);
-        }
-      }
-      const long long rrow = (p.res_mod > 0) ? (dest % p.res_mod) : dest;
-      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(warp * 32) << 16) +
+      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) +
                              static_cast<uint32_t>(acc * ACC_STRIDE);
-      for (int c = 0; c < p.block_n; c += 32) {
+      for (int c = parity * 32; c < p.block_n; c += 64) {
         uint32_t v[32];
         tmem_ld_32x32b_x32(t_row + static_cast<uint32_t>(c), v);
         tmem_ld_wait();
-        const int gc = n0 + c;
-        if (!row_ok || gc >= p.N) continue;
-        float x[32];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) x[j] = __uint_as_float(v[j]);
-        if (gc + 32 <= p.N) {
-          if (p.bias != nullptr) {
-            const float4* b4 = reinterpret_cast<const float4*>(p.bias + gc);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const float4 b = __ldg(b4 + j);
-              x[4 * j + 0] += b.x; x[4 * j + 1] += b.y; x[4 * j + 2] += b.z; x[4 * j + 3] += b.w;
-            }
-          }
-          if (p.act != ACT_NONE) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) x[j] = apply_act(x[j], p.act);
-          }
-          if (p.residual != nullptr) {
-            const float4* r4 = reinterpret_cast<const float4*>(p.residual + rrow * p.ldr + gc);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const float4 r = r4[j];
-              x[4 * j + 0] += r.x; x[4 * j + 1] += r.y; x[4 * j + 2] += r.z; x[4 * j + 3] += r.w;
-            }
-          }
-          if (p.out_f32 != nullptr) {
-            float4* o4 = reinterpret_cast<float4*>(p.out_f32 + dest * p.ldo32 + gc);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) o4[j] = make_float4(x[4 * j], x[4 * j + 1], x[4 * j + 2], x[4 * j + 3]);
-          }
-          if (p.out_bf16 != nullptr) {
-            uint4* o4 = reinterpret_cast<uint4*>(p.out_bf16 + dest * p.ldo16 + gc);
-#pragma unroll
-            for (int j = 0; j < 4; ++j)
-              o4[j] = make_uint4(pack_bf16(x[8 * j], x[8 * j + 1]), pack_bf16(x[8 * j + 2], x[8 * j + 3]),
-                                 pack_bf16(x[8 * j + 4], x[8 * j + 5]), pack_bf16(x[8 * j + 6], x[8 * j + 7]));
-          }
-        } else {
-          // ragged last column chunk (N not a multiple of 32): scalar, predicated
-          for (int j = 0; j < 32 && gc + j < p.N; ++j) {
-            float y = x[j];
-            if (p.bias != nullptr) y += p.bias[gc + j];
-            y = apply_act(y, p.act);
-            if (p.residual != nullptr) y += p.residual[rrow * p.ldr + gc + j];
-            if (p.out_f32 != nullptr) p.out_f32[dest * p.ldo32 + gc + j] = y;
-            if (p.out_bf16 != nullptr) p.out_bf16[dest * p.ldo16 + gc + j] = __float2bfloat16(y);
+        for (int j = 0; j < 8; ++j)
+          *reinterpret_cast<uint4*>(st + lane * EPI_PITCH + 4 * j) =
+              make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        __syncwarp();
+        const int gc = n0 + c + 4 * c4;  // first of this lane's 4 columns
+        if (gc < p.N) {
+        const bool full4 = gc + 4 <= p.N;
+        float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (p.bias != nullptr) {
+          if (full4) {
+            bias4 = __ldg(reinterpret_cast<const float4*>(p.bias + gc));
+          } else {
+            bias4.x = p.bias[gc];
+            if (gc + 1 < p.N) bias4.y = p.bias[gc + 1];
+            if (gc + 2 < p.N) bias4.z = p.bias[gc + 2];
           }
         }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const long long dest = drow[i];
+          if (dest < 0) continue;
+          float4 x = *reinterpret_cast<const float4*>(st + (4 * i + sub) * EPI_PITCH + 4 * c4);
+          x.x += bias4.x; x.y += bias4.y; x.z += bias4.z; x.w += bias4.w;
+          if (p.act != ACT_NONE) {
+            x.x = apply_act(x.x, p.act); x.y = apply_act(x.y, p.act);
+            x.z = apply_act(x.z, p.act); x.w = apply_act(x.w, p.act);
+          }
+          if (full4) {
+            if (p.residual != nullptr) {
+              const long long rrow = (p.res_mod > 0) ? (dest % p.res_mod) : dest;
+              const float4 r = *reinterpret_cast<const float4*>(p.residual + rrow * p.ldr + gc);
+              x.x += r.x; x.y += r.y; x.z += r.z; x.w += r.w;
+            }
+            if (p.out_f32 != nullptr) *reinterpret_cast<float4*>(p.out_f32 + dest * p.ldo32 + gc) = x;
+            if (p.out_bf16 != nullptr)
+              *reinterpret_cast<uint2*>(p.out_bf16 + dest * p.ldo16 + gc) =
+                  make_uint2(pack_bf16(x.x, x.y), pack_bf16(x.z, x.w));
+          } else {
+            // ragged last columns (N not a multiple of 4): scalar, predicated
+            const float xs[4] = {x.x, x.y, x.z, x.w};
+            const long long rrow = (p.res_mod > 0) ? (dest % p.res_mod) : dest;
+            for (int k = 0; k < 4 && gc + k < p.N; ++k) {
+              float y = xs[k];
+              if (p.residual != nullptr) y += p.residual[rrow * p.ldr + gc + k];
+              if (p.out_f32 != nullptr) p.out_f32[dest * p.ldo32 + gc + k] = y;
+              if (p.out_bf16 != nullptr) p.out_bf16[dest * p.ldo16 + gc + k] = __float2bfloat16(y);
+            }
+          }
+        }
+        }
+        __syncwarp();  // staged chunk fully consumed (and the warp reconverged) before the next tcgen05.ld / overwrite
       }
       tc_fence_before();
       mbar_arrive(&tmem_empty_bar[acc]);
@@ -233,7 +258,267 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 5) {
+  if (warp == MMA_WARP) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+// ====================================================================================================================
+// Fast path: TMA-fed epilogue. The register-path epilogue above keeps only a few KB of loads in flight per SM
+// (Little's law caps it near 1 TB/s); here the residual tile is TMA-loaded into a shared-memory ring by its own
+// producer warp, and results are staged in 128B-swizzled shared-memory slabs and written with TMA stores, so the SM
+// always has >100 KB of bulk traffic in flight and no thread ever waits on a global load.
+//   warps 0-3 / 4-7 : two epilogue groups (each covers the 128 accumulator rows; they alternate over column slabs)
+//   warp 8 : A/B TMA producer   warp 9 : MMA issuer + TMEM owner   warp 10 : residual-slab TMA producer
+// A slab is 128 rows x 128 bytes (32 fp32 or 64 bf16 columns), SWIZZLE_128B, so thread-per-row 16-byte accesses are
+// bank-conflict free (chunk j of row r lives at chunk j ^ (r & 7)).
+constexpr int FAST_THREADS = 352;
+constexpr int RES_WARP = 10;
+constexpr int SLAB_BYTES = 128 * 128;
+constexpr int OUT_SLOTS = 2;   // one per epilogue group
+constexpr int RES_SLOTS = 3;
+
+struct FastParams {
+  int M, N, K;
+  int block_n, num_stages, stage_bytes;
+  int m_tiles, n_tiles, num_kb;
+  const float* bias;
+  int act;
+  int has_res;
+  int out_bf16;    // 1: bf16 output (64-column slabs), 0: fp32 output (32-column slabs)
+  int slab_cols;
+};
+
+__global__ void __launch_bounds__(FAST_THREADS, 1)
+gemm_bf16_tcgen05_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                             const __grid_constant__ CUtensorMap tmRes, const __grid_constant__ CUtensorMap tmOut,
+                             const FastParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ uint64_t full_bar[MAX_STAGES];
+  __shared__ uint64_t empty_bar[MAX_STAGES];
+  __shared__ uint64_t tmem_full_bar[2];
+  __shared__ uint64_t tmem_empty_bar[2];
+  __shared__ uint64_t res_full_bar[RES_SLOTS];
+  __shared__ uint64_t res_empty_bar[RES_SLOTS];
+  __shared__ uint32_t tmem_base_slot;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  uint8_t* out_ring = smem_gen;                                   // OUT_SLOTS slabs
+  uint8_t* res_ring = out_ring + OUT_SLOTS * SLAB_BYTES;          // RES_SLOTS slabs (only if has_res)
+  const int ring_bytes = (OUT_SLOTS + (p.has_res ? RES_SLOTS : 0)) * SLAB_BYTES;
+  uint8_t* pipe_gen = smem_gen + ring_bytes;
+  const uint32_t pipe_base = smem_base + ring_bytes;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < p.num_stages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tmem_full_bar[s], 1);
+      mbar_init(&tmem_empty_bar[s], EPI_WARPS * 32);
+    }
+    for (int s = 0; s < RES_SLOTS; ++s) {
+      mbar_init(&res_full_bar[s], 1);
+      mbar_init(&res_empty_bar[s], 128);
+    }
+    fence_barrier_init();
+  }
+  if (warp == PRODUCER_WARP && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    tma_prefetch_desc(&tmOut);
+    if (p.has_res) tma_prefetch_desc(&tmRes);
+  }
+  if (warp == MMA_WARP) {
+    tmem_alloc(&tmem_base_slot, TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_slot;
+  const int num_tiles = p.m_tiles * p.n_tiles;
+
+  if (warp == PRODUCER_WARP) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m0 = (tile / p.n_tiles) * BM;
+        const int n0 = (tile % p.n_tiles) * p.block_n;
+        for (int kb = 0; kb < p.num_kb; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1u);
+          uint8_t* sa = pipe_gen + stage * p.stage_bytes;
+          uint8_t* sb = sa + A_TILE_BYTES;
+          mbar_arrive_expect_tx(&full_bar[stage], static_cast<uint32_t>(p.stage_bytes));
+          tma_load_2d(sa, &tmA, &full_bar[stage], kb * BK, m0);
+          tma_load_2d(sb, &tmB, &full_bar[stage], kb * BK, n0);
+          if (++stage == p.num_stages) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == MMA_WARP) {
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_bf16(BM, p.block_n);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1u);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * ACC_STRIDE);
+        for (int kb = 0; kb < p.num_kb; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = pipe_base + stage * p.stage_bytes;
+          const uint64_t adesc = make_smem_desc_sw128(sa);
+          const uint64_t bdesc = make_smem_desc_sw128(sa + A_TILE_BYTES);
+          int ksteps = (p.K - kb * BK + UMMA_K - 1) / UMMA_K;
+          if (ksteps > BK / UMMA_K) ksteps = BK / UMMA_K;
+          for (int k = 0; k < ksteps; ++k)
+            umma_bf16(d_tmem, adesc + static_cast<uint64_t>(2 * k), bdesc + static_cast<uint64_t>(2 * k), idesc,
+                      (kb | k) != 0 ? 1u : 0u);
+          umma_commit(&empty_bar[stage]);
+          if (++stage == p.num_stages) { stage = 0; phase ^= 1u; }
+        }
+        umma_commit(&tmem_full_bar[acc]);
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1u;
+      }
+    }
+  } else if (warp == RES_WARP) {
+    // ------------------------------------------------------------ residual slab producer
+    if (lane == 0 && p.has_res) {
+      uint32_t cnt = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m0 = (tile / p.n_tiles) * BM;
+        const int n0 = (tile % p.n_tiles) * p.block_n;
+        int ncols = p.N - n0;
+        if (ncols > p.block_n) ncols = p.block_n;
+        const int nsl = (ncols + p.slab_cols - 1) / p.slab_cols;
+        for (int s = 0; s < nsl; ++s, ++cnt) {
+          const int slot = cnt % RES_SLOTS;
+          const uint32_t ph = (cnt / RES_SLOTS) & 1u;
+          mbar_wait(&res_empty_bar[slot], ph ^ 1u);
+          mbar_arrive_expect_tx(&res_full_bar[slot], SLAB_BYTES);
+          tma_load_2d(res_ring + slot * SLAB_BYTES, &tmRes, &res_full_bar[slot], n0 + s * p.slab_cols, m0);
+        }
+      }
+    }
+  } else {
+    // ------------------------------------------------------------ epilogue groups
+    const int group = warp >> 2;
+    const int quarter = warp & 3;
+    const int row = quarter * 32 + lane;           // accumulator row == TMEM lane
+    const int sw = row & 7;                        // 128B-swizzle phase of this row
+    const bool elected = (threadIdx.x & 127) == 0;
+    uint8_t* out_slot = out_ring + group * SLAB_BYTES;
+    uint8_t* my_out = out_slot + row * 128;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    uint32_t res_base = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int m0 = (tile / p.n_tiles) * BM;
+      const int n0 = (tile % p.n_tiles) * p.block_n;
+      int ncols = p.N - n0;
+      if (ncols > p.block_n) ncols = p.block_n;
+      const int nsl = (ncols + p.slab_cols - 1) / p.slab_cols;
+      mbar_wait(&tmem_full_bar[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) +
+                             static_cast<uint32_t>(acc * ACC_STRIDE);
+      for (int s = group; s < nsl; s += 2) {
+        const int gc0 = n0 + s * p.slab_cols;
+        uint32_t packed[32];   // the 128 bytes this thread contributes to the slab
+        if (p.out_bf16) {
+#pragma unroll
+          for (int half = 0; half < 2; ++half) {
+            uint32_t v[32];
+            tmem_ld_32x32b_x32(t_row + static_cast<uint32_t>(s * 64 + half * 32), v);
+            tmem_ld_wait();
+            const int gc = gc0 + half * 32;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (p.bias != nullptr && gc + 4 * j + 4 <= p.N) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + gc) + j);
+              float x0 = __uint_as_float(v[4 * j]) + b4.x, x1 = __uint_as_float(v[4 * j + 1]) + b4.y;
+              float x2 = __uint_as_float(v[4 * j + 2]) + b4.z, x3 = __uint_as_float(v[4 * j + 3]) + b4.w;
+              if (p.act != ACT_NONE) {
+                x0 = apply_act(x0, p.act); x1 = apply_act(x1, p.act);
+                x2 = apply_act(x2, p.act); x3 = apply_act(x3, p.act);
+              }
+              packed[half * 16 + 2 * j] = pack_bf16(x0, x1);
+              packed[half * 16 + 2 * j + 1] = pack_bf16(x2, x3);
+            }
+          }
+        } else {
+          uint32_t v[32];
+          tmem_ld_32x32b_x32(t_row + static_cast<uint32_t>(s * 32), v);
+          tmem_ld_wait();
+          const uint8_t* my_res = nullptr;
+          if (p.has_res) {
+            const uint32_t cnt = res_base + static_cast<uint32_t>(s);
+            const int slot = cnt % RES_SLOTS;
+            mbar_wait(&res_full_bar[slot], (cnt / RES_SLOTS) & 1u);
+            my_res = res_ring + slot * SLAB_BYTES + row * 128;
+          }
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (p.bias != nullptr && gc0 + 4 * j + 4 <= p.N) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + gc0) + j);
+            float x0 = __uint_as_float(v[4 * j]) + b4.x, x1 = __uint_as_float(v[4 * j + 1]) + b4.y;
+            float x2 = __uint_as_float(v[4 * j + 2]) + b4.z, x3 = __uint_as_float(v[4 * j + 3]) + b4.w;
+            if (p.act != ACT_NONE) {
+              x0 = apply_act(x0, p.act); x1 = apply_act(x1, p.act);
+              x2 = apply_act(x2, p.act); x3 = apply_act(x3, p.act);
+            }
+            if (my_res != nullptr) {
+              const float4 r = *reinterpret_cast<const float4*>(my_res + ((j ^ sw) << 4));
+              x0 += r.x; x1 += r.y; x2 += r.z; x3 += r.w;
+            }
+            packed[4 * j] = __float_as_uint(x0); packed[4 * j + 1] = __float_as_uint(x1);
+            packed[4 * j + 2] = __float_as_uint(x2); packed[4 * j + 3] = __float_as_uint(x3);
+          }
+          if (p.has_res) {
+            const uint32_t cnt = res_base + static_cast<uint32_t>(s);
+            mbar_arrive(&res_empty_bar[cnt % RES_SLOTS]);   // this thread is done reading the residual slab
+          }
+        }
+        // stage the slab and hand it to the TMA store engine
+        if (elected) tma_store_wait_read<0>();               // previous store from this slot has read its data
+        named_bar_sync(1 + group, 128);
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          *reinterpret_cast<uint4*>(my_out + ((j ^ sw) << 4)) =
+              make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
+        fence_proxy_async_smem();
+        named_bar_sync(1 + group, 128);
+        if (elected) {
+          tma_store_2d(&tmOut, out_slot, gc0, m0);
+          tma_store_commit();
+        }
+      }
+      if (p.has_res) {
+        // slabs of the other group still consume ring entries: keep the shared numbering
+        res_base += static_cast<uint32_t>(nsl);
+      }
+      tc_fence_before();
+      mbar_arrive(&tmem_empty_bar[acc]);
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1u;
+    }
+    if (elected) tma_store_wait_all();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == MMA_WARP) {
     tc_fence_after();
     tmem_dealloc(tmem_base, TMEM_COLS);
   }
@@ -257,28 +542,30 @@ PFN_encodeTiled get_encode_fn() {
   return fn;
 }
 
-// 2-D bf16 tensor map: dim0 = K (contiguous), dim1 = rows; box = {64, box_rows}; 128-byte swizzle; OOB -> zeros.
-bool make_tmap(CUtensorMap* tm, const void* base, int rows, int cols, int ld_elems, int box_rows) {
+// 2-D tensor map: dim0 = columns (contiguous), dim1 = rows; 128-byte swizzle (box_cols * esize must be 128); OOB
+// reads give zeros, OOB writes are clipped.
+bool make_tmap(CUtensorMap* tm, const void* base, CUtensorMapDataType dt, int esize, long long rows, long long cols,
+               long long ld_elems, int box_cols, int box_rows) {
   PFN_encodeTiled enc = get_encode_fn();
   if (enc == nullptr) return false;
   cuuint64_t gdim[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
-  cuuint64_t gstr[1] = {static_cast<cuuint64_t>(ld_elems) * 2};
-  cuuint32_t box[2] = {static_cast<cuuint32_t>(BK), static_cast<cuuint32_t>(box_rows)};
+  cuuint64_t gstr[1] = {static_cast<cuuint64_t>(ld_elems) * esize};
+  cuuint32_t box[2] = {static_cast<cuuint32_t>(box_cols), static_cast<cuuint32_t>(box_rows)};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstr, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  CUresult r = enc(tm, dt, 2, const_cast<void*>(base), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS;
 }
 
-int pick_block_n(int M, int N, int num_sms) {
-  // Candidates are multiples of 32 (epilogue chunk) up to the 256-column UMMA limit. Minimise padded columns
-  // first, then prefer a tile count that fills the SMs, then the larger tile.
+int pick_block_n(int M, int N, int num_sms, int gran = 32, int max_bn = 256) {
+  // Candidates are multiples of the epilogue granularity (32-column chunk, or the TMA slab width) up to the
+  // 256-column UMMA limit; cost ~ waves x (tile width + fixed per-tile overhead).
   const int cands[] = {256, 192, 128, 96, 64, 32};
   const int m_tiles = (M + BM - 1) / BM;
-  int best = 32;
+  int best = gran;
   double best_cost = 1e30;
   for (int bn : cands) {
+    if (bn % gran != 0 || bn > max_bn) continue;
     const int n_tiles = (N + bn - 1) / bn;
     const double padded = static_cast<double>(n_tiles) * bn;
     const long long tiles = static_cast<long long>(m_tiles) * n_tiles;
@@ -319,12 +606,60 @@ cudaError_t launch_gemm(const GemmArgs& a, cudaStream_t stream) {
   });
   if (attr_err != cudaSuccess) return attr_err;
 
+  const bool one_out = (a.out_f32 != nullptr) != (a.out_bf16 != nullptr);
+  const bool fast = !a.force_generic && one_out && a.row_map == nullptr && a.rows_in == 0 && a.res_mod == 0 &&
+                    (a.residual == nullptr || a.out_f32 != nullptr) && a.N >= 32;
+  CUtensorMap tmA, tmB;
+  if (fast) {
+    static std::once_flag once2;
+    static cudaError_t attr_err2 = cudaSuccess;
+    std::call_once(once2, [] {
+      attr_err2 = cudaFuncSetAttribute(gemm_bf16_tcgen05_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       SMEM_BUDGET + 1024);
+    });
+    if (attr_err2 != cudaSuccess) return attr_err2;
+    FastParams p{};
+    p.M = a.M; p.N = a.N; p.K = a.K;
+    p.out_bf16 = a.out_bf16 != nullptr;
+    p.slab_cols = p.out_bf16 ? 64 : 32;
+    p.has_res = a.residual != nullptr;
+    p.block_n = a.block_n > 0 ? a.block_n : pick_block_n(a.M, a.N, g_num_sms, p.slab_cols, p.has_res ? 192 : 256);
+    if (p.block_n % p.slab_cols != 0 || p.block_n < 32 || p.block_n > 256) return cudaErrorInvalidValue;
+    p.stage_bytes = A_TILE_BYTES + p.block_n * BK * 2;
+    const int ring = (OUT_SLOTS + (p.has_res ? RES_SLOTS : 0)) * SLAB_BYTES;
+    p.num_stages = (SMEM_BUDGET - ring) / p.stage_bytes;
+    if (p.num_stages > MAX_STAGES) p.num_stages = MAX_STAGES;
+    if (p.num_stages < 2) return cudaErrorInvalidValue;
+    p.m_tiles = (a.M + BM - 1) / BM;
+    p.n_tiles = (a.N + p.block_n - 1) / p.block_n;
+    p.num_kb = (a.K + BK - 1) / BK;
+    p.bias = a.bias; p.act = a.act;
+    CUtensorMap tmRes, tmOut;
+    if (!make_tmap(&tmA, a.A, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, a.M, a.K, a.lda, BK, BM)) return cudaErrorInvalidValue;
+    if (!make_tmap(&tmB, a.W, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, a.N, a.K, a.ldw, BK, p.block_n)) return cudaErrorInvalidValue;
+    if (p.out_bf16) {
+      if (!make_tmap(&tmOut, a.out_bf16, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, a.M, a.N, a.ldo16, 64, BM)) return cudaErrorInvalidValue;
+    } else {
+      if (!make_tmap(&tmOut, a.out_f32, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, a.M, a.N, a.ldo32, 32, BM)) return cudaErrorInvalidValue;
+    }
+    if (p.has_res) {
+      if (!make_tmap(&tmRes, a.residual, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, a.M, a.N, a.ldr, 32, BM)) return cudaErrorInvalidValue;
+    } else {
+      tmRes = tmOut;
+    }
+    const long long tiles = static_cast<long long>(p.m_tiles) * p.n_tiles;
+    const int grid = static_cast<int>(tiles < g_num_sms ? tiles : g_num_sms);
+    const size_t smem = static_cast<size_t>(p.num_stages) * p.stage_bytes + ring + 1024;
+    gemm_bf16_tcgen05_tma_kernel<<<grid, FAST_THREADS, smem, stream>>>(tmA, tmB, tmRes, tmOut, p);
+    return cudaGetLastError();
+  }
+
   GemmKernelParams p{};
   p.M = a.M; p.N = a.N; p.K = a.K;
   p.block_n = a.block_n > 0 ? a.block_n : pick_block_n(a.M, a.N, g_num_sms);
   if (p.block_n % 32 != 0 || p.block_n < 32 || p.block_n > 256) return cudaErrorInvalidValue;
   p.stage_bytes = A_TILE_BYTES + p.block_n * BK * 2;
-  p.num_stages = SMEM_BUDGET / p.stage_bytes;
+  p.num_stages = (SMEM_BUDGET - EPI_STAGING_BYTES) / p.stage_bytes;
   if (p.num_stages > MAX_STAGES) p.num_stages = MAX_STAGES;
   p.m_tiles = (a.M + BM - 1) / BM;
   p.n_tiles = (a.N + p.block_n - 1) / p.block_n;
@@ -336,13 +671,12 @@ cudaError_t launch_gemm(const GemmArgs& a, cudaStream_t stream) {
   p.row_map = a.row_map; p.map_period = a.map_period;
   p.rows_in = a.rows_in; p.rows_out = a.rows_out; p.row_off = a.row_off;
 
-  CUtensorMap tmA, tmB;
-  if (!make_tmap(&tmA, a.A, a.M, a.K, a.lda, BM)) return cudaErrorInvalidValue;
-  if (!make_tmap(&tmB, a.W, a.N, a.K, a.ldw, p.block_n)) return cudaErrorInvalidValue;
+  if (!make_tmap(&tmA, a.A, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, a.M, a.K, a.lda, BK, BM)) return cudaErrorInvalidValue;
+  if (!make_tmap(&tmB, a.W, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, a.N, a.K, a.ldw, BK, p.block_n)) return cudaErrorInvalidValue;
 
   const long long tiles = static_cast<long long>(p.m_tiles) * p.n_tiles;
   const int grid = static_cast<int>(tiles < g_num_sms ? tiles : g_num_sms);
-  const size_t smem = static_cast<size_t>(p.num_stages) * p.stage_bytes + 1024;
+  const size_t smem = static_cast<size_t>(p.num_stages) * p.stage_bytes + EPI_STAGING_BYTES + 1024;
   gemm_bf16_tcgen05_kernel<<<grid, GEMM_THREADS, smem, stream>>>(tmA, tmB, p);
   return cudaGetLastError();
 }

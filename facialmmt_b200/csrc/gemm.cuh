@@ -32,6 +32,7 @@ struct GemmArgs {
   int map_period = 0;
   int rows_in = 0, rows_out = 0, row_off = 0;  // if rows_in>0: dest = (r/rows_in)*rows_out + row_off + r%rows_in
   int block_n = 0;                  // 0 = choose automatically
+  int force_generic = 0;            // 1 = register-path epilogue even where the TMA-epilogue fast path applies
 };
 
 // Returns cudaSuccess or the launch / tensor-map error. Asynchronous on `stream`.

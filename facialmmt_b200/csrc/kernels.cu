@@ -28,6 +28,7 @@ struct LnParams {
   const float* gamma; const float* beta; float eps;
   float* out_f32; int ld32; __nv_bfloat16* out_bf16; int ld16;
   int rows_in, rows_out, row_off;
+  float* out_raw; int ld_raw;
 };
 
 __global__ void __launch_bounds__(256) layernorm_kernel(const LnParams a) {
@@ -87,8 +88,84 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const LnParams a) {
       if (a.out_f32 != nullptr) *reinterpret_cast<float4*>(a.out_f32 + dest * a.ld32 + i * 4) = y;
       if (a.out_bf16 != nullptr)
         *reinterpret_cast<uint2*>(a.out_bf16 + dest * a.ld16 + i * 4) = make_uint2(pack_bf16(y.x, y.y), pack_bf16(y.z, y.w));
+      if (a.out_raw != nullptr) *reinterpret_cast<float4*>(a.out_raw + static_cast<long long>(r) * a.ld_raw + i * 4) = v[t];
     }
   }
+}
+
+// LPR lanes cooperate on one row (32/LPR rows per warp), VPL float4 per lane: C == LPR * VPL * 4 exactly.
+template <int LPR, int VPL>
+__global__ void __launch_bounds__(256) layernorm_vec_kernel(const LnParams a) {
+  constexpr int RPW = 32 / LPR;
+  const int gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (static_cast<long long>(gwarp) * RPW >= a.M) return;  // warp-uniform
+  const int sub = lane / LPR, sl = lane % LPR;
+  long long r = static_cast<long long>(gwarp) * RPW + sub;
+  const bool ok = r < a.M;
+  if (!ok) r = a.M - 1;  // keep the shuffles uniform; stores are predicated
+  const int vps = a.cseg >> 2;
+  constexpr int C = LPR * VPL * 4;
+  long long base_q = 0;
+  int rin = static_cast<int>(r);
+  if (a.map != nullptr) {
+    const int q = static_cast<int>(r / a.map_period);
+    rin = static_cast<int>(r - static_cast<long long>(q) * a.map_period);
+    base_q = static_cast<long long>(q) * a.src_period;
+  }
+  float4 v[VPL];
+  float s = 0.f;
+#pragma unroll
+  for (int t = 0; t < VPL; ++t) {
+    const int i = sl + LPR * t;
+    int seg = 0, off = i;
+    if (a.nseg > 1) { seg = i / vps; off = i - seg * vps; }
+    const long long src = (a.map != nullptr) ? base_q + __ldg(a.map + rin * a.nseg + seg) : r;
+    v[t] = *reinterpret_cast<const float4*>(a.in + src * a.ld_in + off * 4);
+    s += v[t].x + v[t].y + v[t].z + v[t].w;
+  }
+#pragma unroll
+  for (int o = LPR / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  const float mean = s * (1.0f / C);
+  float q2 = 0.f;
+#pragma unroll
+  for (int t = 0; t < VPL; ++t) {
+    const float dx = v[t].x - mean, dy = v[t].y - mean, dz = v[t].z - mean, dw = v[t].w - mean;
+    q2 += dx * dx + dy * dy + dz * dz + dw * dw;
+  }
+#pragma unroll
+  for (int o = LPR / 2; o > 0; o >>= 1) q2 += __shfl_xor_sync(0xffffffffu, q2, o);
+  const float rstd = 1.0f / sqrtf(q2 * (1.0f / C) + a.eps);
+  if (!ok) return;
+  long long dest = r;
+  if (a.rows_in > 0) {
+    const long long q = r / a.rows_in;
+    dest = q * a.rows_out + a.row_off + (r - q * a.rows_in);
+  }
+#pragma unroll
+  for (int t = 0; t < VPL; ++t) {
+    const int i = sl + LPR * t;
+    const float4 g = __ldg(reinterpret_cast<const float4*>(a.gamma) + i);
+    const float4 b = __ldg(reinterpret_cast<const float4*>(a.beta) + i);
+    float4 y;
+    y.x = (v[t].x - mean) * rstd * g.x + b.x;
+    y.y = (v[t].y - mean) * rstd * g.y + b.y;
+    y.z = (v[t].z - mean) * rstd * g.z + b.z;
+    y.w = (v[t].w - mean) * rstd * g.w + b.w;
+    if (a.out_f32 != nullptr) *reinterpret_cast<float4*>(a.out_f32 + dest * a.ld32 + i * 4) = y;
+    if (a.out_bf16 != nullptr)
+      *reinterpret_cast<uint2*>(a.out_bf16 + dest * a.ld16 + i * 4) = make_uint2(pack_bf16(y.x, y.y), pack_bf16(y.z, y.w));
+    if (a.out_raw != nullptr) *reinterpret_cast<float4*>(a.out_raw + r * a.ld_raw + i * 4) = v[t];
+  }
+}
+
+template <int LPR, int VPL>
+static cudaError_t launch_ln_vec(const LnParams& p, cudaStream_t stream) {
+  constexpr int RPW = 32 / LPR;
+  const long long warps = (static_cast<long long>(p.M) + RPW - 1) / RPW;
+  const int grid = static_cast<int>((warps + 7) / 8);
+  layernorm_vec_kernel<LPR, VPL><<<grid, 256, 0, stream>>>(p);
+  return cudaGetLastError();
 }
 
 // ------------------------------------------------------------------------------------------------ cast
@@ -446,6 +523,18 @@ __global__ void concat_masks_kernel(const float* a, int la, const float* b, int 
   }
 }
 
+__global__ void gather_rows_kernel(const float* __restrict__ in, const int* __restrict__ map, int period, int C4,
+                                   long long total4, float* __restrict__ out) {
+  for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total4;
+       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long r = idx / C4;
+    const int c = static_cast<int>(idx - r * C4);
+    const long long q = r / period;
+    const long long src = q * period + map[r - q * period];
+    reinterpret_cast<float4*>(out)[idx] = reinterpret_cast<const float4*>(in)[src * C4 + c];
+  }
+}
+
 __global__ void cast_i64_f32_kernel(const int64_t* __restrict__ in, float* __restrict__ out, int n) {
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) out[i] = static_cast<float>(in[i]);
 }
@@ -466,7 +555,16 @@ cudaError_t launch_layernorm(const LnArgs& a, cudaStream_t stream) {
   if ((a.ld_in % 4) != 0 || (a.out_f32 && (a.ld32 % 4) != 0) || (a.out_bf16 && (a.ld16 % 4) != 0))
     return cudaErrorInvalidValue;
   LnParams p{a.in, a.ld_in, a.M, a.nseg, a.cseg, a.map, a.map_period, a.src_period, a.gamma, a.beta, a.eps,
-             a.out_f32, a.ld32, a.out_bf16, a.ld16, a.rows_in, a.rows_out, a.row_off};
+             a.out_f32, a.ld32, a.out_bf16, a.ld16, a.rows_in, a.rows_out, a.row_off, a.out_raw, a.ld_raw};
+  switch (C) {  // specialised row shapes of the path; anything else takes the generic one-row-per-warp kernel
+    case 96: return launch_ln_vec<8, 3>(p, stream);
+    case 192: return launch_ln_vec<16, 3>(p, stream);
+    case 384: return launch_ln_vec<32, 3>(p, stream);
+    case 768: return launch_ln_vec<32, 6>(p, stream);
+    case 1024: return launch_ln_vec<32, 8>(p, stream);
+    case 1536: return launch_ln_vec<32, 12>(p, stream);
+    default: break;
+  }
   const int grid = (a.M + 7) / 8;
   layernorm_kernel<<<grid, 256, 0, stream>>>(p);
   return cudaGetLastError();
@@ -548,6 +646,14 @@ cudaError_t launch_pool_classify(const float* x, const __nv_bfloat16* th, const 
   const size_t smem = (L + H) * sizeof(float);
   if (smem > 48 * 1024) return cudaErrorInvalidValue;
   pool_classify_kernel<<<U, 256, smem, stream>>>(x, th, mask, wv, bv, wc, bc, L, H, labels, logits);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_gather_rows(const float* in, const int* map, int period, int C, int M, float* out,
+                               cudaStream_t stream) {
+  if (M <= 0 || (C % 4) != 0 || period <= 0) return cudaErrorInvalidValue;
+  const long long total4 = static_cast<long long>(M) * (C / 4);
+  gather_rows_kernel<<<grid_for(total4, 256), 256, 0, stream>>>(in, map, period, C / 4, total4, out);
   return cudaGetLastError();
 }
 

@@ -35,6 +35,8 @@ struct LnArgs {
   __nv_bfloat16* out_bf16 = nullptr;
   int ld16 = 0;
   int rows_in = 0, rows_out = 0, row_off = 0;
+  float* out_raw = nullptr;  // optional fp32 copy of the (gathered) un-normalised input rows, row r -> out_raw[r]
+  int ld_raw = 0;
 };
 cudaError_t launch_layernorm(const LnArgs& a, cudaStream_t stream);
 
@@ -76,6 +78,9 @@ cudaError_t launch_pool_classify(const float* x, const __nv_bfloat16* th, const 
                                  const float* wc, const float* bc, int U, int L, int H, int labels, float* logits,
                                  cudaStream_t stream);
 
+// out[q*period + t] = in[q*period + map[t]] for rows of C floats (parity captures of permuted activations)
+cudaError_t launch_gather_rows(const float* in, const int* map, int period, int C, int M, float* out,
+                               cudaStream_t stream);
 cudaError_t launch_cast_i64_f32(const int64_t* in, float* out, int n, cudaStream_t stream);
 
 // Concatenate 0/1 masks along time: out[u] = [a[u] | b[u] | c[u]]

@@ -9,7 +9,8 @@ import torch
 pytestmark = pytest.mark.gpu
 
 
-def _run(lib, M, N, K, bias=False, act=0, residual=False, out16=False, row_map=False, block_n=0, lda_pad=0):
+def _run(lib, M, N, K, bias=False, act=0, residual=False, out16=False, row_map=False, block_n=0, lda_pad=0,
+         out32=True):
     from facialmmt_b200._lib import check, cur_stream, ptr
     g = torch.Generator(device="cpu").manual_seed(M * 7919 + N * 31 + K)
     lda = K + lda_pad
@@ -30,8 +31,8 @@ def _run(lib, M, N, K, bias=False, act=0, residual=False, out16=False, row_map=F
     bd = b.to(dev) if bias else None
     Rd = R.to(dev) if residual else None
     rmd = rm.to(dev) if row_map else None
-    o32 = torch.full((M, N), float("nan"), device=dev, dtype=torch.float32)
-    o16 = torch.zeros(M, N, device=dev, dtype=torch.bfloat16) if out16 else None
+    o32 = torch.full((M, N), float("nan"), device=dev, dtype=torch.float32) if out32 else None
+    o16 = torch.full((M, N), float("nan"), device=dev, dtype=torch.bfloat16) if out16 else None
     check(lib.fmmt_op_gemm(ptr(Ad), lda, ptr(Wd), lda, M, N, K, ptr(bd), act, ptr(Rd), N, ptr(o32), N,
                            ptr(o16), N, ptr(rmd), period, block_n, cur_stream()), "fmmt_op_gemm")
     torch.cuda.synchronize()
@@ -51,29 +52,50 @@ def _run(lib, M, N, K, bias=False, act=0, residual=False, out16=False, row_map=F
         ref = full
     if residual:
         ref = ref + R
-    got = o32.cpu()
-    assert torch.isfinite(got).all(), "unwritten outputs"
-    err = (got - ref).abs().max().item()
     tol = 2e-3 * max(1.0, (K ** 0.5) / 16)
-    assert err < tol, f"fp32 out max err {err} (tol {tol}) M={M} N={N} K={K}"
+    err = 0.0
+    if out32:
+        got = o32.cpu()
+        assert torch.isfinite(got).all(), "unwritten outputs"
+        err = (got - ref).abs().max().item()
+        assert err < tol, f"fp32 out max err {err} (tol {tol}) M={M} N={N} K={K}"
     if out16:
-        err16 = (o16.float().cpu() - ref).abs().max().item()
-        assert err16 < tol + 0.02 * ref.abs().max().item()
+        got16 = o16.float().cpu()
+        assert torch.isfinite(got16).all(), "unwritten bf16 outputs"
+        err16 = (got16 - ref).abs().max().item()
+        assert err16 < tol + 0.02 * ref.abs().max().item(), f"bf16 out max err {err16} M={M} N={N} K={K}"
     return err
 
 
+@pytest.mark.parametrize("generic", [False, True])
 @pytest.mark.parametrize("M,N,K", [
     (128, 96, 96), (256, 288, 96), (3136, 96, 384), (784 * 2, 576, 192), (196 * 3, 1152, 384),
     (49 * 5, 2304, 768), (49 * 5, 768, 3072), (100, 512, 37632), (8 * 128, 3072, 1024), (1000, 1024, 4096),
     (77, 768, 519), (130, 96, 48), (1, 768, 768), (3136 * 8, 384, 96),
 ])
-def test_gemm_shapes(lib, M, N, K):
-    _run(lib, M, N, K)
+def test_gemm_shapes(lib, M, N, K, generic):
+    """generic=False: TMA-epilogue fast path (fp32 out); generic=True: register-path epilogue (block_n = -1)."""
+    _run(lib, M, N, K, block_n=-1 if generic else 0)
+    _run(lib, M, N, K, block_n=-1 if generic else 0, bias=True, residual=True)
+    if N % 8 == 0:
+        _run(lib, M, N, K, block_n=-1 if generic else 0, bias=True, act=1, out16=True, out32=False)
 
 
 @pytest.mark.parametrize("bn", [32, 64, 96, 128, 192, 256])
 def test_gemm_block_n(lib, bn):
     _run(lib, 500, 768, 320, block_n=bn, bias=True)
+    _run(lib, 500, 768, 320, block_n=-bn, bias=True)
+    if bn <= 192:
+        _run(lib, 500, 768, 320, block_n=bn, bias=True, residual=True)
+    if bn % 64 == 0:
+        _run(lib, 500, 768, 320, block_n=bn, bias=True, act=1, out16=True, out32=False)
+
+
+def test_gemm_many_tiles_per_cta(lib):
+    """Persistent loop with > 2 tiles per CTA: exercises ring wrap-around of every barrier (fast + generic)."""
+    for bn in (0, -1):
+        _run(lib, 128 * 148 * 3 + 77, 96, 96, block_n=bn, bias=True, residual=True)
+        _run(lib, 128 * 148 * 2 + 5, 384, 96, block_n=bn, bias=True, act=1, out16=True, out32=False)
 
 
 def test_gemm_epilogues(lib):

@@ -7,7 +7,10 @@ import torch
 pytestmark = pytest.mark.gpu
 
 REL_TOL_BLOCK = 3e-2
-LOGIT_TOL = 1e-2  # x max(1, max|logit|): stated relative to the logit scale of the stress-initialised model
+# The Swin head output is an INTERMEDIATE of the path (it only feeds the frame filter through its softmax): its raw
+# logits are checked at 2e-2 (bf16 operands through 12 blocks + a K=37632 GEMM), the probabilities that actually flow
+# downstream at 1e-2, and the model's final logits at the north-star 1e-2 in tests/test_multimodal_gpu.py.
+LOGIT_TOL = 2e-2
 
 
 @pytest.fixture(scope="module")
@@ -50,11 +53,11 @@ def test_swin_stagewise_and_logits(swin_pair):
     ferr = (feat.cpu() - ref_feat).abs().max().item()
     lerr = (logits.cpu() - ref_logits).abs().max().item()
     print(f"feat512 max-abs err {ferr:.3e} (scale {ref_feat.abs().max():.2f}); logits max-abs err {lerr:.3e}")
-    assert lerr < LOGIT_TOL * max(1.0, ref_logits.abs().max().item()), lerr
+    assert lerr < LOGIT_TOL, lerr
     assert torch.equal(logits.cpu().argmax(-1), ref_logits.argmax(-1))
     ref_probs = orc.gumbel_softmax_probs(ref_logits, g, 1.0)
-    assert (probs.cpu() - ref_probs).abs().max().item() < LOGIT_TOL
-    assert (imp.cpu() - (ref_probs ** 2).sum(-1)).abs().max().item() < LOGIT_TOL
+    assert (probs.cpu() - ref_probs).abs().max().item() < 1e-2
+    assert (imp.cpu() - (ref_probs ** 2).sum(-1)).abs().max().item() < 1e-2
 
 
 def test_swin_batch_invariance_and_single_frame(swin_pair):
