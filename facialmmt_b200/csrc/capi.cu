@@ -116,6 +116,8 @@ FMMT_API int64_t fmmt_profile_read(fmmt_handle* h, char* buf, int64_t buf_len) {
   return static_cast<int64_t>(js.size() + 1);
 }
 
+FMMT_API uint32_t fmmt_debug_timeout(int reset) { return read_mbar_timeout(reset != 0); }
+
 FMMT_API double fmmt_flops(fmmt_handle* h, int reset) { return h ? h->eng->flops(reset != 0) : 0.0; }
 FMMT_API int64_t fmmt_device_bytes(fmmt_handle* h) { return h ? h->eng->device_bytes() : 0; }
 

@@ -273,11 +273,15 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
 //   warp 8 : A/B TMA producer   warp 9 : MMA issuer + TMEM owner   warp 10 : residual-slab TMA producer
 // A slab is 128 rows x 128 bytes (32 fp32 or 64 bf16 columns), SWIZZLE_128B, so thread-per-row 16-byte accesses are
 // bank-conflict free (chunk j of row r lives at chunk j ^ (r & 7)).
-constexpr int FAST_THREADS = 352;
-constexpr int RES_WARP = 10;
+constexpr int EPI_GROUPS = 4;                       // 4 groups x 4 warps: every SMSP hosts 4 epilogue warps
+constexpr int FAST_EPI_WARPS = 4 * EPI_GROUPS;
+constexpr int FAST_PRODUCER_WARP = FAST_EPI_WARPS;
+constexpr int FAST_MMA_WARP = FAST_EPI_WARPS + 1;
+constexpr int FAST_RES_WARP = FAST_EPI_WARPS + 2;
+constexpr int FAST_THREADS = (FAST_EPI_WARPS + 3) * 32;   // 608
 constexpr int SLAB_BYTES = 128 * 128;
-constexpr int OUT_SLOTS = 2;   // one per epilogue group
-constexpr int RES_SLOTS = 3;
+constexpr int OUT_SLOTS = EPI_GROUPS;   // one staging slab per epilogue group
+constexpr int RES_SLOTS = EPI_GROUPS;   // slot g is produced for / consumed by group g only
 
 struct FastParams {
   int M, N, K;
@@ -290,6 +294,31 @@ struct FastParams {
   int slab_cols;
 };
 
+template <int ACT>
+__device__ __forceinline__ float act_fn(float x, int act_rt) {
+  if (ACT == ACT_NONE) return x;
+  if (ACT == ACT_GELU) return gelu_erf(x);
+  return apply_act(x, act_rt);
+}
+
+// bias + activation on 32 accumulator columns of this thread's row, in place (v holds fp32 bit patterns)
+template <int ACT>
+__device__ __forceinline__ void epi_math32(uint32_t (&v)[32], const float* bias, int gc, int N, int act_rt) {
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (bias != nullptr && gc + 4 * j + 4 <= N) b4 = __ldg(reinterpret_cast<const float4*>(bias + gc) + j);
+    v[4 * j + 0] = __float_as_uint(act_fn<ACT>(__uint_as_float(v[4 * j + 0]) + b4.x, act_rt));
+    v[4 * j + 1] = __float_as_uint(act_fn<ACT>(__uint_as_float(v[4 * j + 1]) + b4.y, act_rt));
+    v[4 * j + 2] = __float_as_uint(act_fn<ACT>(__uint_as_float(v[4 * j + 2]) + b4.z, act_rt));
+    v[4 * j + 3] = __float_as_uint(act_fn<ACT>(__uint_as_float(v[4 * j + 3]) + b4.w, act_rt));
+  }
+}
+__device__ __forceinline__ uint32_t pack_bf16_bits(uint32_t a, uint32_t b) {
+  return pack_bf16(__uint_as_float(a), __uint_as_float(b));
+}
+
+template <int ACT>
 __global__ void __launch_bounds__(FAST_THREADS, 1)
 gemm_bf16_tcgen05_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                              const __grid_constant__ CUtensorMap tmRes, const __grid_constant__ CUtensorMap tmOut,
@@ -320,7 +349,7 @@ gemm_bf16_tcgen05_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __gr
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tmem_full_bar[s], 1);
-      mbar_init(&tmem_empty_bar[s], EPI_WARPS * 32);
+      mbar_init(&tmem_empty_bar[s], FAST_EPI_WARPS * 32);
     }
     for (int s = 0; s < RES_SLOTS; ++s) {
       mbar_init(&res_full_bar[s], 1);
@@ -328,13 +357,13 @@ gemm_bf16_tcgen05_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __gr
     }
     fence_barrier_init();
   }
-  if (warp == PRODUCER_WARP && lane == 0) {
+  if (warp == FAST_PRODUCER_WARP && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
     tma_prefetch_desc(&tmOut);
     if (p.has_res) tma_prefetch_desc(&tmRes);
   }
-  if (warp == MMA_WARP) {
+  if (warp == FAST_MMA_WARP) {
     tmem_alloc(&tmem_base_slot, TMEM_COLS);
     tmem_relinquish();
   }
@@ -344,7 +373,7 @@ gemm_bf16_tcgen05_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __gr
   const uint32_t tmem_base = tmem_base_slot;
   const int num_tiles = p.m_tiles * p.n_tiles;
 
-  if (warp == PRODUCER_WARP) {
+  if (warp == FAST_PRODUCER_WARP) {
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
@@ -352,7 +381,7 @@ gemm_bf16_tcgen05_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __gr
         const int m0 = (tile / p.n_tiles) * BM;
         const int n0 = (tile % p.n_tiles) * p.block_n;
         for (int kb = 0; kb < p.num_kb; ++kb) {
-          mbar_wait(&empty_bar[stage], phase ^ 1u);
+          mbar_wait(&empty_bar[stage], phase ^ 1u, 1);
           uint8_t* sa = pipe_gen + stage * p.stage_bytes;
           uint8_t* sb = sa + A_TILE_BYTES;
           mbar_arrive_expect_tx(&full_bar[stage], static_cast<uint32_t>(p.stage_bytes));
@@ -362,7 +391,7 @@ gemm_bf16_tcgen05_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __gr
         }
       }
     }
-  } else if (warp == MMA_WARP) {
+  } else if (warp == FAST_MMA_WARP) {
     if (lane == 0) {
       const uint32_t idesc = make_idesc_bf16(BM, p.block_n);
       int stage = 0;
@@ -370,11 +399,11 @@ gemm_bf16_tcgen05_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __gr
       int acc = 0;
       uint32_t acc_phase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1u);
+        mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1u, 2);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * ACC_STRIDE);
         for (int kb = 0; kb < p.num_kb; ++kb) {
-          mbar_wait(&full_bar[stage], phase);
+          mbar_wait(&full_bar[stage], phase, 3);
           tc_fence_after();
           const uint32_t sa = pipe_base + stage * p.stage_bytes;
           const uint64_t adesc = make_smem_desc_sw128(sa);
@@ -392,7 +421,7 @@ gemm_bf16_tcgen05_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __gr
         if (acc == 0) acc_phase ^= 1u;
       }
     }
-  } else if (warp == RES_WARP) {
+  } else if (warp == FAST_RES_WARP) {
     // ------------------------------------------------------------ residual slab producer
     if (lane == 0 && p.has_res) {
       uint32_t cnt = 0;
@@ -405,7 +434,7 @@ gemm_bf16_tcgen05_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __gr
         for (int s = 0; s < nsl; ++s, ++cnt) {
           const int slot = cnt % RES_SLOTS;
           const uint32_t ph = (cnt / RES_SLOTS) & 1u;
-          mbar_wait(&res_empty_bar[slot], ph ^ 1u);
+          mbar_wait(&res_empty_bar[slot], ph ^ 1u, 4);
           mbar_arrive_expect_tx(&res_full_bar[slot], SLAB_BYTES);
           tma_load_2d(res_ring + slot * SLAB_BYTES, &tmRes, &res_full_bar[slot], n0 + s * p.slab_cols, m0);
         }
@@ -429,74 +458,61 @@ gemm_bf16_tcgen05_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __gr
       int ncols = p.N - n0;
       if (ncols > p.block_n) ncols = p.block_n;
       const int nsl = (ncols + p.slab_cols - 1) / p.slab_cols;
-      mbar_wait(&tmem_full_bar[acc], acc_phase);
+      mbar_wait(&tmem_full_bar[acc], acc_phase, 5);
       tc_fence_after();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) +
                              static_cast<uint32_t>(acc * ACC_STRIDE);
-      for (int s = group; s < nsl; s += 2) {
+      // Slab with running number c = res_base + s goes to group c % EPI_GROUPS (== its residual-ring slot): work
+      // rotates over the groups from tile to tile, and every group consumes EVERY use of "its" ring slot in order,
+      // which is what makes the parity waits on res_full/res_empty alias-free.
+      for (int s = static_cast<int>((static_cast<uint32_t>(group) - res_base) % EPI_GROUPS); s < nsl; s += EPI_GROUPS) {
         const int gc0 = n0 + s * p.slab_cols;
-        uint32_t packed[32];   // the 128 bytes this thread contributes to the slab
         if (p.out_bf16) {
+          uint32_t v[32];
+          tmem_ld_32x32b_x32(t_row + static_cast<uint32_t>(s * 64), v);
+          tmem_ld_wait();
+          epi_math32<ACT>(v, p.bias, gc0, p.N, p.act);
+          if (elected) tma_store_wait_read<0>();             // previous store from this slot has read its data
+          named_bar_sync(1 + group, 128);
 #pragma unroll
-          for (int half = 0; half < 2; ++half) {
-            uint32_t v[32];
-            tmem_ld_32x32b_x32(t_row + static_cast<uint32_t>(s * 64 + half * 32), v);
-            tmem_ld_wait();
-            const int gc = gc0 + half * 32;
+          for (int j = 0; j < 4; ++j)
+            *reinterpret_cast<uint4*>(my_out + ((j ^ sw) << 4)) =
+                make_uint4(pack_bf16_bits(v[8 * j], v[8 * j + 1]), pack_bf16_bits(v[8 * j + 2], v[8 * j + 3]),
+                           pack_bf16_bits(v[8 * j + 4], v[8 * j + 5]), pack_bf16_bits(v[8 * j + 6], v[8 * j + 7]));
+          tmem_ld_32x32b_x32(t_row + static_cast<uint32_t>(s * 64 + 32), v);
+          tmem_ld_wait();
+          epi_math32<ACT>(v, p.bias, gc0 + 32, p.N, p.act);
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
-              if (p.bias != nullptr && gc + 4 * j + 4 <= p.N) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + gc) + j);
-              float x0 = __uint_as_float(v[4 * j]) + b4.x, x1 = __uint_as_float(v[4 * j + 1]) + b4.y;
-              float x2 = __uint_as_float(v[4 * j + 2]) + b4.z, x3 = __uint_as_float(v[4 * j + 3]) + b4.w;
-              if (p.act != ACT_NONE) {
-                x0 = apply_act(x0, p.act); x1 = apply_act(x1, p.act);
-                x2 = apply_act(x2, p.act); x3 = apply_act(x3, p.act);
-              }
-              packed[half * 16 + 2 * j] = pack_bf16(x0, x1);
-              packed[half * 16 + 2 * j + 1] = pack_bf16(x2, x3);
-            }
-          }
+          for (int j = 0; j < 4; ++j)
+            *reinterpret_cast<uint4*>(my_out + (((4 + j) ^ sw) << 4)) =
+                make_uint4(pack_bf16_bits(v[8 * j], v[8 * j + 1]), pack_bf16_bits(v[8 * j + 2], v[8 * j + 3]),
+                           pack_bf16_bits(v[8 * j + 4], v[8 * j + 5]), pack_bf16_bits(v[8 * j + 6], v[8 * j + 7]));
         } else {
           uint32_t v[32];
           tmem_ld_32x32b_x32(t_row + static_cast<uint32_t>(s * 32), v);
           tmem_ld_wait();
-          const uint8_t* my_res = nullptr;
+          epi_math32<ACT>(v, p.bias, gc0, p.N, p.act);
           if (p.has_res) {
             const uint32_t cnt = res_base + static_cast<uint32_t>(s);
             const int slot = cnt % RES_SLOTS;
-            mbar_wait(&res_full_bar[slot], (cnt / RES_SLOTS) & 1u);
-            my_res = res_ring + slot * SLAB_BYTES + row * 128;
-          }
+            mbar_wait(&res_full_bar[slot], (cnt / RES_SLOTS) & 1u, 6);
+            const uint8_t* my_res = res_ring + slot * SLAB_BYTES + row * 128;
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (p.bias != nullptr && gc0 + 4 * j + 4 <= p.N) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + gc0) + j);
-            float x0 = __uint_as_float(v[4 * j]) + b4.x, x1 = __uint_as_float(v[4 * j + 1]) + b4.y;
-            float x2 = __uint_as_float(v[4 * j + 2]) + b4.z, x3 = __uint_as_float(v[4 * j + 3]) + b4.w;
-            if (p.act != ACT_NONE) {
-              x0 = apply_act(x0, p.act); x1 = apply_act(x1, p.act);
-              x2 = apply_act(x2, p.act); x3 = apply_act(x3, p.act);
-            }
-            if (my_res != nullptr) {
+            for (int j = 0; j < 8; ++j) {
               const float4 r = *reinterpret_cast<const float4*>(my_res + ((j ^ sw) << 4));
-              x0 += r.x; x1 += r.y; x2 += r.z; x3 += r.w;
+              v[4 * j] = __float_as_uint(__uint_as_float(v[4 * j]) + r.x);
+              v[4 * j + 1] = __float_as_uint(__uint_as_float(v[4 * j + 1]) + r.y);
+              v[4 * j + 2] = __float_as_uint(__uint_as_float(v[4 * j + 2]) + r.z);
+              v[4 * j + 3] = __float_as_uint(__uint_as_float(v[4 * j + 3]) + r.w);
             }
-            packed[4 * j] = __float_as_uint(x0); packed[4 * j + 1] = __float_as_uint(x1);
-            packed[4 * j + 2] = __float_as_uint(x2); packed[4 * j + 3] = __float_as_uint(x3);
+            mbar_arrive(&res_empty_bar[slot]);               // this thread is done reading the residual slab
           }
-          if (p.has_res) {
-            const uint32_t cnt = res_base + static_cast<uint32_t>(s);
-            mbar_arrive(&res_empty_bar[cnt % RES_SLOTS]);   // this thread is done reading the residual slab
-          }
-        }
-        // stage the slab and hand it to the TMA store engine
-        if (elected) tma_store_wait_read<0>();               // previous store from this slot has read its data
-        named_bar_sync(1 + group, 128);
+          if (elected) tma_store_wait_read<0>();
+          named_bar_sync(1 + group, 128);
 #pragma unroll
-        for (int j = 0; j < 8; ++j)
-          *reinterpret_cast<uint4*>(my_out + ((j ^ sw) << 4)) =
-              make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
+          for (int j = 0; j < 8; ++j)
+            *reinterpret_cast<uint4*>(my_out + ((j ^ sw) << 4)) = make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        }
         fence_proxy_async_smem();
         named_bar_sync(1 + group, 128);
         if (elected) {
@@ -504,10 +520,7 @@ gemm_bf16_tcgen05_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __gr
           tma_store_commit();
         }
       }
-      if (p.has_res) {
-        // slabs of the other group still consume ring entries: keep the shared numbering
-        res_base += static_cast<uint32_t>(nsl);
-      }
+      res_base += static_cast<uint32_t>(nsl);
       tc_fence_before();
       mbar_arrive(&tmem_empty_bar[acc]);
       acc ^= 1;
@@ -518,7 +531,7 @@ gemm_bf16_tcgen05_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __gr
 
   tc_fence_before();
   __syncthreads();
-  if (warp == MMA_WARP) {
+  if (warp == FAST_MMA_WARP) {
     tc_fence_after();
     tmem_dealloc(tmem_base, TMEM_COLS);
   }
@@ -585,6 +598,16 @@ int g_num_sms = 0;
 
 }  // namespace
 
+unsigned int read_mbar_timeout(bool reset) {
+  unsigned int v = 0;
+  cudaMemcpyFromSymbol(&v, g_mbar_timeout, sizeof(v));
+  if (reset && v != 0) {
+    unsigned int z = 0;
+    cudaMemcpyToSymbol(g_mbar_timeout, &z, sizeof(z));
+  }
+  return v;
+}
+
 cudaError_t launch_gemm(const GemmArgs& a, cudaStream_t stream) {
   if (a.M <= 0 || a.N <= 0 || a.K <= 0) return cudaErrorInvalidValue;
   if ((a.lda % 8) != 0 || (a.ldw % 8) != 0) return cudaErrorInvalidValue;  // TMA: 16-byte global strides
@@ -614,8 +637,14 @@ cudaError_t launch_gemm(const GemmArgs& a, cudaStream_t stream) {
     static std::once_flag once2;
     static cudaError_t attr_err2 = cudaSuccess;
     std::call_once(once2, [] {
-      attr_err2 = cudaFuncSetAttribute(gemm_bf16_tcgen05_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       SMEM_BUDGET + 1024);
+      attr_err2 = cudaFuncSetAttribute(gemm_bf16_tcgen05_tma_kernel<ACT_NONE>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BUDGET + 1024);
+      if (attr_err2 == cudaSuccess)
+        attr_err2 = cudaFuncSetAttribute(gemm_bf16_tcgen05_tma_kernel<ACT_GELU>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BUDGET + 1024);
+      if (attr_err2 == cudaSuccess)
+        attr_err2 = cudaFuncSetAttribute(gemm_bf16_tcgen05_tma_kernel<ACT_TANH>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BUDGET + 1024);
     });
     if (attr_err2 != cudaSuccess) return attr_err2;
     FastParams p{};
@@ -623,7 +652,7 @@ cudaError_t launch_gemm(const GemmArgs& a, cudaStream_t stream) {
     p.out_bf16 = a.out_bf16 != nullptr;
     p.slab_cols = p.out_bf16 ? 64 : 32;
     p.has_res = a.residual != nullptr;
-    p.block_n = a.block_n > 0 ? a.block_n : pick_block_n(a.M, a.N, g_num_sms, p.slab_cols, p.has_res ? 192 : 256);
+    p.block_n = a.block_n > 0 ? a.block_n : pick_block_n(a.M, a.N, g_num_sms, p.slab_cols, p.has_res ? 128 : 256);
     if (p.block_n % p.slab_cols != 0 || p.block_n < 32 || p.block_n > 256) return cudaErrorInvalidValue;
     p.stage_bytes = A_TILE_BYTES + p.block_n * BK * 2;
     const int ring = (OUT_SLOTS + (p.has_res ? RES_SLOTS : 0)) * SLAB_BYTES;
@@ -650,7 +679,12 @@ cudaError_t launch_gemm(const GemmArgs& a, cudaStream_t stream) {
     const long long tiles = static_cast<long long>(p.m_tiles) * p.n_tiles;
     const int grid = static_cast<int>(tiles < g_num_sms ? tiles : g_num_sms);
     const size_t smem = static_cast<size_t>(p.num_stages) * p.stage_bytes + ring + 1024;
-    gemm_bf16_tcgen05_tma_kernel<<<grid, FAST_THREADS, smem, stream>>>(tmA, tmB, tmRes, tmOut, p);
+    if (a.act == ACT_NONE)
+      gemm_bf16_tcgen05_tma_kernel<ACT_NONE><<<grid, FAST_THREADS, smem, stream>>>(tmA, tmB, tmRes, tmOut, p);
+    else if (a.act == ACT_GELU)
+      gemm_bf16_tcgen05_tma_kernel<ACT_GELU><<<grid, FAST_THREADS, smem, stream>>>(tmA, tmB, tmRes, tmOut, p);
+    else  // runtime-switched activation (ReLU / tanh)
+      gemm_bf16_tcgen05_tma_kernel<ACT_TANH><<<grid, FAST_THREADS, smem, stream>>>(tmA, tmB, tmRes, tmOut, p);
     return cudaGetLastError();
   }
 

@@ -38,6 +38,10 @@ struct GemmArgs {
 // Returns cudaSuccess or the launch / tensor-map error. Asynchronous on `stream`.
 cudaError_t launch_gemm(const GemmArgs& a, cudaStream_t stream);
 
+// Non-zero if a pipeline wait inside a GEMM kernel timed out since the last reset (a protocol bug): bit 31 set,
+// bits 24-30 = which barrier, 12-23 = CTA, 0-11 = thread. Synchronises the device.
+unsigned int read_mbar_timeout(bool reset);
+
 // Algorithmic work of one launch (2*M*N*K) for roofline accounting.
 inline double gemm_flops(const GemmArgs& a) { return 2.0 * a.M * (double)a.N * a.K; }
 

@@ -42,11 +42,21 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return done != 0;
 }
-// Bounded spin: a protocol bug traps (-> CUDA error on the host) instead of hanging the GPU.
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+// Bounded spin: a protocol bug must never hang the GPU. On timeout the waiter records who it was in a global word
+// (read back through fmmt_debug_timeout()) and every other waiter bails out as soon as it sees the word set, so the
+// kernel terminates (with wrong results) and the host reports the failure.
+__device__ unsigned int g_mbar_timeout = 0;
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, uint32_t tag = 0) {
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (++spins > (1u << 26)) __trap();
+    ++spins;
+    if ((spins & 0x3FFF) == 0) {
+      if (*reinterpret_cast<volatile unsigned int*>(&g_mbar_timeout) != 0) return;
+      if (spins > (1u << 24)) {
+        atomicCAS(&g_mbar_timeout, 0u, 0x80000000u | (tag << 24) | ((blockIdx.x & 0xFFF) << 12) | (threadIdx.x & 0xFFF));
+        return;
+      }
+    }
   }
 }
 

@@ -121,6 +121,10 @@ FMMT_API int fmmt_set_capture(fmmt_handle* h, const char* name, float* dst, int6
  * profiling was enabled; returns the number of bytes needed (including the terminating NUL). */
 FMMT_API int fmmt_set_profile(fmmt_handle* h, int enable);
 FMMT_API int64_t fmmt_profile_read(fmmt_handle* h, char* buf, int64_t buf_len);
+/* Pipeline watchdog: non-zero if an mbarrier wait inside a GEMM kernel timed out since the last reset (a protocol bug;
+ * the kernel then terminates with wrong results instead of hanging). Bit 31 set, bits 24-30 barrier id, 12-23 CTA,
+ * 0-11 thread. Synchronises the device. */
+FMMT_API uint32_t fmmt_debug_timeout(int reset);
 /* Algorithmic FLOPs (2*MAC of every GEMM/attention launched) accumulated by the handle since the last reset. */
 FMMT_API double fmmt_flops(fmmt_handle* h, int reset);
 /* Bytes of device memory held by the handle (weights + workspace). */

@@ -116,3 +116,12 @@ def test_gemm_rejects_bad_alignment(lib):
                           cur_stream())
     assert rc != 0
     assert b"invalid" in lib.fmmt_last_error()
+
+
+@pytest.mark.parametrize("N,K,res,out16", [(96, 96, True, False), (96, 48, False, False), (128, 96, True, False),
+                                           (288, 96, False, True), (384, 96, False, True), (96, 384, True, False)])
+def test_gemm_streaming_many_tiles(lib, N, K, res, out16):
+    """Stage-1 Swin shapes at chunk scale (784 m-tiles, > 5 per CTA), repeated: epilogue-bound streaming where the
+    residual/out rings and the slab->group assignment cycle many times (regression for a ring-parity aliasing bug)."""
+    for _ in range(4):
+        _run(lib, 100352, N, K, bias=True, residual=res, out16=out16, out32=not out16, act=1 if out16 else 0)
