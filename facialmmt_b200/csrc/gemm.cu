@@ -280,7 +280,6 @@ constexpr int FAST_MMA_WARP = FAST_EPI_WARPS + 1;
 constexpr int FAST_RES_WARP = FAST_EPI_WARPS + 2;
 constexpr int FAST_THREADS = (FAST_EPI_WARPS + 3) * 32;   // 608
 constexpr int SLAB_BYTES = 128 * 128;
-constexpr int OUT_SLOTS = EPI_GROUPS;   // one staging slab per epilogue group
 constexpr int RES_SLOTS = EPI_GROUPS;   // slot g is produced for / consumed by group g only
 
 struct FastParams {
@@ -292,6 +291,8 @@ struct FastParams {
   int has_res;
   int out_bf16;    // 1: bf16 output (64-column slabs), 0: fp32 output (32-column slabs)
   int slab_cols;
+  int groups;      // active epilogue groups (2 or 4) == staging slabs == residual ring slots: compute-heavy GEMMs
+                   // (large K) give the shared memory to the A/B pipeline instead of the epilogue rings
 };
 
 template <int ACT>
@@ -336,9 +337,9 @@ gemm_bf16_tcgen05_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __gr
   const int lane = threadIdx.x & 31;
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
-  uint8_t* out_ring = smem_gen;                                   // OUT_SLOTS slabs
-  uint8_t* res_ring = out_ring + OUT_SLOTS * SLAB_BYTES;          // RES_SLOTS slabs (only if has_res)
-  const int ring_bytes = (OUT_SLOTS + (p.has_res ? RES_SLOTS : 0)) * SLAB_BYTES;
+  uint8_t* out_ring = smem_gen;                                   // p.groups slabs
+  uint8_t* res_ring = out_ring + p.groups * SLAB_BYTES;           // p.groups slabs (only if has_res)
+  const int ring_bytes = (p.has_res ? 2 : 1) * p.groups * SLAB_BYTES;
   uint8_t* pipe_gen = smem_gen + ring_bytes;
   const uint32_t pipe_base = smem_base + ring_bytes;
 
@@ -432,8 +433,8 @@ gemm_bf16_tcgen05_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __gr
         if (ncols > p.block_n) ncols = p.block_n;
         const int nsl = (ncols + p.slab_cols - 1) / p.slab_cols;
         for (int s = 0; s < nsl; ++s, ++cnt) {
-          const int slot = cnt % RES_SLOTS;
-          const uint32_t ph = (cnt / RES_SLOTS) & 1u;
+          const int slot = cnt % p.groups;
+          const uint32_t ph = (cnt / p.groups) & 1u;
           mbar_wait(&res_empty_bar[slot], ph ^ 1u, 4);
           mbar_arrive_expect_tx(&res_full_bar[slot], SLAB_BYTES);
           tma_load_2d(res_ring + slot * SLAB_BYTES, &tmRes, &res_full_bar[slot], n0 + s * p.slab_cols, m0);
@@ -465,7 +466,10 @@ gemm_bf16_tcgen05_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __gr
       // Slab with running number c = res_base + s goes to group c % EPI_GROUPS (== its residual-ring slot): work
       // rotates over the groups from tile to tile, and every group consumes EVERY use of "its" ring slot in order,
       // which is what makes the parity waits on res_full/res_empty alias-free.
-      for (int s = static_cast<int>((static_cast<uint32_t>(group) - res_base) % EPI_GROUPS); s < nsl; s += EPI_GROUPS) {
+      const uint32_t ng = static_cast<uint32_t>(p.groups);
+      int s_first = nsl;   // inactive groups only take part in the accumulator hand-shake
+      if (group < p.groups) s_first = static_cast<int>((static_cast<uint32_t>(group) + ng - res_base % ng) % ng);
+      for (int s = s_first; s < nsl; s += p.groups) {
         const int gc0 = n0 + s * p.slab_cols;
         if (p.out_bf16) {
           uint32_t v[32];
@@ -494,8 +498,8 @@ gemm_bf16_tcgen05_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __gr
           epi_math32<ACT>(v, p.bias, gc0, p.N, p.act);
           if (p.has_res) {
             const uint32_t cnt = res_base + static_cast<uint32_t>(s);
-            const int slot = cnt % RES_SLOTS;
-            mbar_wait(&res_full_bar[slot], (cnt / RES_SLOTS) & 1u, 6);
+            const int slot = cnt % p.groups;   // == group
+            mbar_wait(&res_full_bar[slot], (cnt / p.groups) & 1u, 6);
             const uint8_t* my_res = res_ring + slot * SLAB_BYTES + row * 128;
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
@@ -652,10 +656,16 @@ cudaError_t launch_gemm(const GemmArgs& a, cudaStream_t stream) {
     p.out_bf16 = a.out_bf16 != nullptr;
     p.slab_cols = p.out_bf16 ? 64 : 32;
     p.has_res = a.residual != nullptr;
-    p.block_n = a.block_n > 0 ? a.block_n : pick_block_n(a.M, a.N, g_num_sms, p.slab_cols, p.has_res ? 128 : 256);
+    p.block_n = a.block_n > 0 ? a.block_n : pick_block_n(a.M, a.N, g_num_sms, p.slab_cols, 256);
     if (p.block_n % p.slab_cols != 0 || p.block_n < 32 || p.block_n > 256) return cudaErrorInvalidValue;
     p.stage_bytes = A_TILE_BYTES + p.block_n * BK * 2;
-    const int ring = (OUT_SLOTS + (p.has_res ? RES_SLOTS : 0)) * SLAB_BYTES;
+    // epilogue-bound shapes (small K) want all 4 groups; compute-bound ones want pipeline depth
+    p.groups = (a.K >= 512) ? 2 : EPI_GROUPS;
+    int ring = (p.has_res ? 2 : 1) * p.groups * SLAB_BYTES;
+    if ((SMEM_BUDGET - ring) / p.stage_bytes < 3 && p.groups > 2) {
+      p.groups = 2;
+      ring = (p.has_res ? 2 : 1) * p.groups * SLAB_BYTES;
+    }
     p.num_stages = (SMEM_BUDGET - ring) / p.stage_bytes;
     if (p.num_stages > MAX_STAGES) p.num_stages = MAX_STAGES;
     if (p.num_stages < 2) return cudaErrorInvalidValue;
