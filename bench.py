@@ -259,11 +259,13 @@ def run_ours(args):
     total_ms, gpu_launches = timed(step_device, args.steps, args.warmup)
     clocks = sampler.stop() if rank == 0 else None
     e2e_steps = max(2, args.steps // 2)
-    e2e_ms, _ = timed(step_e2e, e2e_steps, 1)
+    e2e_ms = float("nan")
+    if not args.no_e2e:
+        e2e_ms, _ = timed(step_e2e, e2e_steps, 1)
 
     # ---- per-kernel event profile of one extra step (same stream) for the roofline object
     roof = None
-    if rank == 0:
+    if rank == 0 and not args.no_e2e:
         swin.set_profile(True)
         mm.set_profile(True)
         step_device()
@@ -326,6 +328,7 @@ def main():
     ap.add_argument("--swin-chunk", type=int, default=0)
     ap.add_argument("--swin-chunk-late", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer end-to-end leg (profiling runs)")
     ap.add_argument("--profile-out", default=None, help="write the per-kernel event profile of one step as JSON")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":

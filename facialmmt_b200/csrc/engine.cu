@@ -761,8 +761,8 @@ void Engine::swin_body(const float* frames, int F, const float* gumbel, float ta
   const size_t FL = static_cast<size_t>(sl.R) * sl.R * sl.C;
   bf16* feat_ln = arena_.alloc<bf16>(static_cast<size_t>(F) * FL);
   float* feat512 = arena_.alloc<float>(static_cast<size_t>(F) * c.feat_dim);
-  const int big = c.swin_chunk_late > 0 ? c.swin_chunk_late : 64;
-  const int small = c.swin_chunk > 0 ? c.swin_chunk : 16;
+  const int big = c.swin_chunk_late > 0 ? c.swin_chunk_late : 160;   // measured best on B200 (profiles/)
+  const int small = c.swin_chunk > 0 ? c.swin_chunk : 64;
   const SwinStageW& ss = swin_.stages[split];
   const size_t per_frame_split = static_cast<size_t>(ss.R) * ss.R * ss.C;
   for (int f0 = 0; f0 < F; f0 += big) {

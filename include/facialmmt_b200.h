@@ -76,8 +76,9 @@ FMMT_API int64_t fmmt_launch_count(void);
 FMMT_API int fmmt_create(const fmmt_config* cfg, fmmt_handle** out);
 FMMT_API void fmmt_destroy(fmmt_handle* h);
 /* Stage one tensor of the reference state_dict under its reference key name. `data` is a HOST pointer to contiguous
- * fp32; shape/ndim as in the state_dict. Unknown keys are rejected with FMMT_ERR_INVALID (integer buffers such as
- * relative_position_index / num_batches_tracked / position_ids are recomputed and must not be passed). */
+ * fp32; shape/ndim as in the state_dict. Keys the path does not use are stored and ignored; integer buffers such as
+ * relative_position_index / num_batches_tracked / position_ids are recomputed and need not be passed. A key that
+ * fmmt_finalize needs and does not find makes it fail with FMMT_ERR_STATE naming the key. */
 FMMT_API int fmmt_load_weight(fmmt_handle* h, const char* ref_key, const float* data, const int64_t* shape, int ndim);
 /* Pack to device: bf16 K-major weights, fused QKV, BatchNorm folded into Linear(37632,512), relative-position bias
  * expanded to (heads,49,49), shift-region ids, window/merge gather maps, sinusoid table. Synchronous. */
