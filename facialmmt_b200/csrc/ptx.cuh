@@ -72,6 +72,25 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* t
       : "memory");
 }
 
+// Multicast variant: the box lands at the same CTA-relative offset in every CTA of `cta_mask`, and each of those
+// CTAs' mbarrier (same offset) receives the complete_tx for the bytes written into it.
+__device__ __forceinline__ void tma_load_2d_mc(void* smem_dst, const CUtensorMap* tm, uint64_t* bar, int c0, int c1,
+                                               uint16_t cta_mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster"
+      " [%0], [%1, {%4, %5}], [%2], %3;" ::"r"(smem_u32(smem_dst)),
+      "l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(bar)), "h"(cta_mask), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.aligned;\n\tbarrier.cluster.wait.aligned;" ::: "memory");
+}
+
 // 2-D tiled store shared -> global (bulk async group); OOB parts of the box are clipped.
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* tm, const void* smem_src, int c0, int c1) {
   asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
@@ -122,6 +141,13 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
                : "memory");
 }
+// Same, arriving on the mbarrier at this offset in every CTA of `cta_mask` (releases a multicast-fed smem slot).
+__device__ __forceinline__ void umma_commit_mc(uint64_t* bar, uint16_t cta_mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::
+                   "r"(smem_u32(bar)),
+               "h"(cta_mask)
+               : "memory");
+}
 // TMEM -> registers: this warp's 32 lanes x 32 consecutive fp32 columns (thread i gets lane i).
 __device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t (&v)[32]) {
   asm volatile(
@@ -161,21 +187,20 @@ __host__ __device__ __forceinline__ uint32_t make_idesc_bf16(int m, int n) {
 }
 
 // ---------------------------------------------------------------- misc
-// erf via Abramowitz-Stegun 7.1.26 (|abs err| <= 1.5e-7, far below the bf16 rounding of every consumer): one
-// reciprocal, one exp, five FMAs instead of the ~30-instruction erff.
-__device__ __forceinline__ float erf_as(float x) {
-  const float ax = fabsf(x);
-  const float t = __fdividef(1.0f, fmaf(0.3275911f, ax, 1.0f));
-  float y = fmaf(t, 1.061405429f, -1.453152027f);
-  y = fmaf(t, y, 1.421413741f);
-  y = fmaf(t, y, -0.284496736f);
-  y = fmaf(t, y, 0.254829592f);
-  y *= t;
-  const float r = 1.0f - y * __expf(-ax * ax);
-  return copysignf(r, x);
+// Exact-erf GELU (nn.GELU(), F.gelu, modules/Transformer.py:119-124): 0.5*x*(1+erf(x/sqrt2)).
+// erfc(z) = 2^P(z) on z = |x|/sqrt2 in [0, 4.2] with a degree-5 polynomial fitted to log2(erfc) (max |gelu error|
+// 1.4e-6 in fp32 over the whole real line, i.e. erff-grade), so one GELU costs 6 FMA + one MUFU.EX2 instead of the
+// ~30-instruction erff or a reciprocal + exp. The negative branch uses 0.5*x*erfc(z) directly: no cancellation.
+__device__ __forceinline__ float gelu_erf(float x) {
+  const float z = fminf(fabsf(x) * 0.70710678118654752f, 4.2f);
+  float p = fmaf(z, -2.98332428e-03f, 2.97336457e-02f);
+  p = fmaf(z, p, -1.48837507e-01f);
+  p = fmaf(z, p, -9.18433869e-01f);
+  p = fmaf(z, p, -1.62789775e+00f);
+  p = fmaf(z, p, -2.71726947e-07f);
+  const float h = 0.5f * x * exp2f(p);          // 0.5 * x * erfc(|x|/sqrt2), same sign as x
+  return fmaxf(x, 0.0f) - fabsf(h);
 }
-// exact-erf GELU (nn.GELU(), F.gelu, modules/Transformer.py:119-124)
-__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erf_as(x * 0.70710678118654752f)); }
 
 __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
   __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
