@@ -9,6 +9,7 @@
 #include "gemm.cuh"
 #include "ptx.cuh"
 
+#include <cmath>
 #include <mutex>
 
 namespace fmmt {
@@ -574,22 +575,24 @@ bool make_tmap(CUtensorMap* tm, const void* base, CUtensorMapDataType dt, int es
   return r == CUDA_SUCCESS;
 }
 
-int pick_block_n(int M, int N, int num_sms, int gran = 32, int max_bn = 256) {
+int pick_block_n(int M, int N, int K, int num_sms, int gran = 32, int max_bn = 256) {
   // Candidates are multiples of the epilogue granularity (32-column chunk, or the TMA slab width) up to the
-  // 256-column UMMA limit; cost ~ waves x (tile width + fixed per-tile overhead).
-  const int cands[] = {256, 192, 128, 96, 64, 32};
+  // 256-column UMMA limit. Cost model fitted to B200 sweeps (tests/gpu_gemm_shapes.py, SWEEP=1): a tile costs a fixed
+  // ~0.9 us (barrier round trips, TMEM drain, store hand-off) plus the larger of its operand feed ((128 + bn) rows of
+  // K bf16 at ~45 B/ns per SM) and its epilogue (~6 ns per output column); the launch costs waves x tile.
+  const int cands[] = {256, 224, 192, 160, 128, 96, 64, 32};
   const int m_tiles = (M + BM - 1) / BM;
   int best = gran;
   double best_cost = 1e30;
   for (int bn : cands) {
     if (bn % gran != 0 || bn > max_bn) continue;
     const int n_tiles = (N + bn - 1) / bn;
-    const double padded = static_cast<double>(n_tiles) * bn;
     const long long tiles = static_cast<long long>(m_tiles) * n_tiles;
-    const long long waves = (tiles + num_sms - 1) / num_sms;
-    // time ~ waves * (tile cost ~ bn columns + fixed per-tile overhead); padded columns are paid for as tile cost
-    (void)padded;
-    const double cost = static_cast<double>(waves) * (bn + 24.0);
+    const double waves = static_cast<double>(tiles) / num_sms;
+    const double waves_q = waves < 1.0 ? 1.0 : (waves > 4.0 ? waves : std::ceil(waves));
+    const double feed = (128.0 + bn) * K * 2.0 / 45e3;
+    const double epi = 0.006 * bn;
+    const double cost = waves_q * (0.9 + (feed > epi ? feed : epi));
     if (cost < best_cost - 1e-9) {
       best_cost = cost;
       best = bn;
@@ -656,7 +659,7 @@ cudaError_t launch_gemm(const GemmArgs& a, cudaStream_t stream) {
     p.out_bf16 = a.out_bf16 != nullptr;
     p.slab_cols = p.out_bf16 ? 64 : 32;
     p.has_res = a.residual != nullptr;
-    p.block_n = a.block_n > 0 ? a.block_n : pick_block_n(a.M, a.N, g_num_sms, p.slab_cols, 256);
+    p.block_n = a.block_n > 0 ? a.block_n : pick_block_n(a.M, a.N, a.K, g_num_sms, p.slab_cols, 256);
     if (p.block_n % p.slab_cols != 0 || p.block_n < 32 || p.block_n > 256) return cudaErrorInvalidValue;
     p.stage_bytes = A_TILE_BYTES + p.block_n * BK * 2;
     // epilogue-bound shapes (small K) want all 4 groups; compute-bound ones want pipeline depth
@@ -700,7 +703,7 @@ cudaError_t launch_gemm(const GemmArgs& a, cudaStream_t stream) {
 
   GemmKernelParams p{};
   p.M = a.M; p.N = a.N; p.K = a.K;
-  p.block_n = a.block_n > 0 ? a.block_n : pick_block_n(a.M, a.N, g_num_sms);
+  p.block_n = a.block_n > 0 ? a.block_n : pick_block_n(a.M, a.N, a.K, g_num_sms);
   if (p.block_n % 32 != 0 || p.block_n < 32 || p.block_n > 256) return cudaErrorInvalidValue;
   p.stage_bytes = A_TILE_BYTES + p.block_n * BK * 2;
   p.num_stages = (SMEM_BUDGET - EPI_STAGING_BYTES) / p.stage_bytes;

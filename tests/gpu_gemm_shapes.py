@@ -10,6 +10,7 @@ shapes = [(200704, 288, 96, 0, 1, 0), (200704, 384, 96, 0, 1, 1), (200704, 96, 9
           (31360, 1152, 384, 0, 1, 0), (31360, 1536, 384, 0, 1, 1), (31360, 384, 1536, 1, 0, 0), (31360, 384, 384, 1, 0, 0),
           (7840, 3072, 768, 0, 1, 1), (7840, 768, 3072, 1, 0, 0), (1024, 4096, 1024, 0, 1, 1), (1024, 1024, 4096, 1, 0, 0)]
 tot = 0
+sweep = os.environ.get("SWEEP", "0") == "1"
 for (M, N, K, res, o16, act) in shapes:
     A = torch.randn(M, K, device="cuda").to(torch.bfloat16)
     W = torch.randn(N, K, device="cuda").to(torch.bfloat16)
@@ -17,15 +18,27 @@ for (M, N, K, res, o16, act) in shapes:
     R = torch.randn(M, N, device="cuda") if res else None
     o32 = None if o16 else torch.empty(M, N, device="cuda")
     ob = torch.empty(M, N, device="cuda", dtype=torch.bfloat16) if o16 else None
-    def run():
-        check(lib.fmmt_op_gemm(ptr(A), K, ptr(W), K, M, N, K, ptr(b), act, ptr(R), N, ptr(o32), N, ptr(ob), N, None, 0, 0, cur_stream()))
-    for _ in range(3): run()
-    torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(20): run()
-    e1.record(); torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / 20
+    def timeit(bn):
+        def run():
+            check(lib.fmmt_op_gemm(ptr(A), K, ptr(W), K, M, N, K, ptr(b), act, ptr(R), N, ptr(o32), N, ptr(ob), N, None, 0, bn, cur_stream()))
+        for _ in range(3): run()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(20): run()
+        e1.record(); torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / 20
+    ms = timeit(0)
+    if sweep:
+        gran = 64 if o16 else 32
+        res_s = []
+        for bn in (32, 64, 96, 128, 160, 192, 224, 256):
+            if bn % gran: continue
+            try:
+                res_s.append((bn, timeit(bn) * 1000))
+            except Exception as e:
+                res_s.append((bn, float("nan")))
+        print("   sweep block_n:", ", ".join(f"{bn}:{t:.1f}" for bn, t in res_s))
     fl = 2.0 * M * N * K
     by = 2.0 * (M * K + N * K) + (2 if o16 else 4) * M * N + (4 * M * N if res else 0)
     tot += ms
