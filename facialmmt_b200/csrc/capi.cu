@@ -4,6 +4,7 @@
 #include <cstring>
 #include <new>
 #include <string>
+#include <vector>
 
 #include "engine.cuh"
 
@@ -116,7 +117,11 @@ FMMT_API int64_t fmmt_profile_read(fmmt_handle* h, char* buf, int64_t buf_len) {
   return static_cast<int64_t>(js.size() + 1);
 }
 
-FMMT_API uint32_t fmmt_debug_timeout(int reset) { return read_mbar_timeout(reset != 0); }
+FMMT_API uint32_t fmmt_debug_timeout(int reset) {
+  const uint32_t a = read_mbar_timeout(reset != 0);
+  const uint32_t b = read_mlp_timeout(reset != 0);
+  return a != 0 ? a : b;
+}
 
 FMMT_API double fmmt_flops(fmmt_handle* h, int reset) { return h ? h->eng->flops(reset != 0) : 0.0; }
 FMMT_API int64_t fmmt_device_bytes(fmmt_handle* h) { return h ? h->eng->device_bytes() : 0; }
@@ -153,6 +158,23 @@ FMMT_API int fmmt_op_layernorm(const float* in, int ld_in, int M, int nseg, int 
   a.out_bf16 = static_cast<__nv_bfloat16*>(out_bf16); a.ld16 = ld16;
   count_launch();
   return check_cuda(launch_layernorm(a, S(stream)), "fmmt_op_layernorm");
+}
+
+FMMT_API int fmmt_op_swin_mlp_pack(const float* fc1_w_host, const float* fc2_w_host, void* img_dev) {
+  if (!fc1_w_host || !fc2_w_host || !img_dev) return set_error(FMMT_ERR_INVALID, "fmmt_op_swin_mlp_pack: null pointer");
+  std::vector<__nv_bfloat16> img(MLP96_IMG_BYTES / sizeof(__nv_bfloat16));
+  mlp96_pack_weights(fc1_w_host, fc2_w_host, img.data());
+  return check_cuda(cudaMemcpy(img_dev, img.data(), MLP96_IMG_BYTES, cudaMemcpyHostToDevice), "fmmt_op_swin_mlp_pack");
+}
+
+FMMT_API int fmmt_op_swin_mlp(float* x, int M, const float* gamma, const float* beta, float eps, const void* img_dev,
+                              const float* b1, const float* b2, void* stream) {
+  if (!x || !gamma || !beta || !img_dev || !b1 || !b2) return set_error(FMMT_ERR_INVALID, "fmmt_op_swin_mlp: null pointer");
+  Mlp96Args a;
+  a.x = x; a.M = M; a.gamma = gamma; a.beta = beta; a.eps = eps;
+  a.img = static_cast<const __nv_bfloat16*>(img_dev); a.b1 = b1; a.b2 = b2;
+  count_launch();
+  return check_cuda(launch_mlp96(a, S(stream)), "fmmt_op_swin_mlp");
 }
 
 FMMT_API int fmmt_op_window_attention(const void* qkv_bf16, void* out_bf16, const float* bias, const int8_t* rid,

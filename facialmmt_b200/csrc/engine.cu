@@ -4,6 +4,7 @@
 #include <atomic>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <stdexcept>
 
@@ -207,6 +208,12 @@ void Engine::pack_swin() {
       expect(bw.qkv.N == 3 * C && bw.qkv.K == C && bw.proj.N == C && bw.fc1.K == C && bw.fc2.N == C &&
                  bw.fc2.K == bw.fc1.N && bw.ln1.C == C,
              p + " dims");
+      if (C == MLP96_C && bw.fc1.N == MLP96_H && bw.fc1.b && bw.fc2.b && std::getenv("FMMT_NO_FUSED_MLP") == nullptr) {
+        std::vector<bf16> img(MLP96_IMG_BYTES / sizeof(bf16));
+        mlp96_pack_weights(need(p + "mlp.fc1.weight").data.data(), need(p + "mlp.fc2.weight").data.data(), img.data());
+        bw.mlp_img = dev_alloc<bf16>(img.size());
+        cudaMemcpy(bw.mlp_img, img.data(), MLP96_IMG_BYTES, cudaMemcpyHostToDevice);
+      }
       const HostTensor& tab = need(p + "attn.relative_position_bias_table");
       const int span = 2 * sw.ws - 1;
       expect(tab.numel() == static_cast<int64_t>(span) * span * sw.heads, p + "relative_position_bias_table");
@@ -563,6 +570,21 @@ void Engine::ln(LnArgs a) {
   if (prof_) prof_end(e1);
 }
 
+void Engine::mlp96(float* x, int M, const SwinBlockW& bw) {
+  if (arena_.dry() || first_err_ != cudaSuccess) return;
+  flops_ += mlp96_flops(M);
+  count_launch();
+  cudaEvent_t e1 = nullptr;
+  // algorithmic bytes: x read once, x updated once (the reduce-add reads it again inside the memory system), weights
+  if (prof_) e1 = prof_begin("mlp_fused C=96 M=" + std::to_string(M), mlp96_flops(M), 8.0 * M * MLP96_C + MLP96_IMG_BYTES);
+  Mlp96Args a;
+  a.x = x; a.M = M;
+  a.gamma = bw.ln2.g; a.beta = bw.ln2.b; a.eps = 1e-5f;
+  a.img = bw.mlp_img; a.b1 = bw.fc1.b; a.b2 = bw.fc2.b;
+  ck(launch_mlp96(a, st_), "mlp_fused");
+  if (prof_) prof_end(e1);
+}
+
 void Engine::capture(const std::string& name, const float* src, size_t count, size_t dst_off) {
   if (arena_.dry() || first_err_ != cudaSuccess || caps_.empty()) return;
   auto it = caps_.find(name);
@@ -655,6 +677,10 @@ void Engine::swin_block(const SwinStageW& sw, const SwinBlockW& bw, float*& x, f
   GemmArgs g2;                                                      // proj + shortcut, in window order (no scatter)
   g2.residual = x; g2.ldr = C; g2.out_f32 = x; g2.ldo32 = C;
   gemm_lin(a, C, M, bw.proj, g2);
+  if (bw.mlp_img != nullptr) {                                      // stage 1: norm2 + fc1 + GELU + fc2 + residual fused
+    mlp96(x, M, bw);
+    return;
+  }
   LnArgs l2;
   l2.in = x; l2.ld_in = C; l2.M = M; l2.cseg = C;
   l2.gamma = bw.ln2.g; l2.beta = bw.ln2.b; l2.eps = 1e-5f;

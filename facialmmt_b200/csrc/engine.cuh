@@ -11,6 +11,7 @@
 
 #include "facialmmt_b200.h"
 #include "gemm.cuh"
+#include "mlp_fused.cuh"
 #include "ops.cuh"
 
 namespace fmmt {
@@ -42,6 +43,7 @@ struct Norm {
 struct SwinBlockW {
   Norm ln1, ln2;
   Lin qkv, proj, fc1, fc2;
+  bf16* mlp_img = nullptr;    // C == 96: fc1/fc2 pre-swizzled for the fused MLP kernel (mlp_fused.cu), else nullptr
   float* bias_exp = nullptr;  // [heads, N, N]
   int shift = 0;
   // The residual stream is kept in the window order of the most recent attention block, so that every GEMM output
@@ -176,6 +178,7 @@ class Engine {
   void gemm(GemmArgs a);
   void gemm_lin(const bf16* A, int lda, int M, const Lin& l, GemmArgs ep);
   void ln(LnArgs a);
+  void mlp96(float* x, int M, const SwinBlockW& bw);
   void ck(cudaError_t e, const char* what);
   void capture(const std::string& name, const float* src, size_t count, size_t dst_off = 0);
 

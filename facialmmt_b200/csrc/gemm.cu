@@ -605,6 +605,11 @@ int g_num_sms = 0;
 
 }  // namespace
 
+bool make_tmap_2d(CUtensorMap* tm, const void* base, CUtensorMapDataType dt, int esize, long long rows, long long cols,
+                  long long ld_elems, int box_cols, int box_rows) {
+  return make_tmap(tm, base, dt, esize, rows, cols, ld_elems, box_cols, box_rows);
+}
+
 unsigned int read_mbar_timeout(bool reset) {
   unsigned int v = 0;
   cudaMemcpyFromSymbol(&v, g_mbar_timeout, sizeof(v));

@@ -1,5 +1,6 @@
 // Host-side interface of the tcgen05 GEMM used by every Linear layer on the path.
 #pragma once
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
 #include <stdint.h>
@@ -37,6 +38,11 @@ struct GemmArgs {
 
 // Returns cudaSuccess or the launch / tensor-map error. Asynchronous on `stream`.
 cudaError_t launch_gemm(const GemmArgs& a, cudaStream_t stream);
+
+// 2-D SWIZZLE_128B tensor map over a row-major matrix (dim0 = columns, dim1 = rows; box_cols * esize must be 128).
+// OOB reads give zeros, OOB writes are clipped. Shared with the fused kernels (mlp_fused.cu).
+bool make_tmap_2d(CUtensorMap* tm, const void* base, CUtensorMapDataType dt, int esize, long long rows, long long cols,
+                  long long ld_elems, int box_cols, int box_rows);
 
 // Non-zero if a pipeline wait inside a GEMM kernel timed out since the last reset (a protocol bug): bit 31 set,
 // bits 24-30 = which barrier, 12-23 = CTA, 0-11 = thread. Synchronises the device.

@@ -150,6 +150,15 @@ FMMT_API int fmmt_op_layernorm(const float* in, int ld_in, int M, int nseg, int 
 FMMT_API int fmmt_op_window_attention(const void* qkv_bf16, void* out_bf16, const float* bias, const int8_t* rid,
                                       int num_windows, int nW, int heads, int C, int N, float scale, void* stream);
 
+/* Fused Swin MLP half-block for C = 96, hidden = 384 (Swin_Transformer.py:24-30 Mlp.forward inside :264-268):
+ *   x <- x + fc2(GELU_erf(fc1(LayerNorm(x; gamma, beta, eps))))        x: fp32 [M, 96] on the device, updated IN PLACE.
+ * fmmt_op_swin_mlp_pack turns the reference's fc1.weight (384,96) / fc2.weight (96,384) (HOST fp32, nn.Linear layout)
+ * into the 147456-byte bf16 shared-memory image the kernel keeps resident (img_dev: device buffer of that size). */
+#define FMMT_MLP96_IMG_BYTES 147456
+FMMT_API int fmmt_op_swin_mlp_pack(const float* fc1_w_host, const float* fc2_w_host, void* img_dev);
+FMMT_API int fmmt_op_swin_mlp(float* x, int M, const float* gamma, const float* beta, float eps, const void* img_dev,
+                              const float* b1, const float* b2, void* stream);
+
 /* Multi-head attention core, head_dim 64: softmax(scale * q k^T + (1 - key_mask) * mask_neg) v.
  * q rows (b*Lq+i), k/v rows (b*Lk+j), head h at columns [64h, 64h+64). key_mask fp32 (B,Lk) of 0/1 or NULL. */
 FMMT_API int fmmt_op_mha(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv, void* out, int ldo,

@@ -12,7 +12,10 @@ cfg = FmmtConfig()
 m = SwinForAffwildClassification(cfg, swin_chunk=F, swin_chunk_late=F)
 m.load_state_dict(syn.swin_cls_stress_state_dict(cfg.swin, 1111))
 x = torch.rand(F, 3, 224, 224, device="cuda") * 2 - 1
-for _ in range(2):
-    m(x, is_trg_task=False)
+m(x, is_trg_task=False)
 torch.cuda.synchronize()
+torch.cuda.profiler.start()   # ncu --profile-from-start off captures only this pass
+m(x, is_trg_task=False)
+torch.cuda.synchronize()
+torch.cuda.profiler.stop()
 print("done")
