@@ -23,6 +23,21 @@ __device__ __forceinline__ void ldmatrix_x4_trans(uint32_t (&r)[4], const void* 
                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
                : "r"(smem_u32(smem_ptr)));
 }
+__device__ __forceinline__ void ldmatrix_x4_s(uint32_t (&r)[4], uint32_t saddr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(saddr));
+}
+__device__ __forceinline__ void ldmatrix_x4_trans_s(uint32_t (&r)[4], uint32_t saddr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(saddr));
+}
+__device__ __forceinline__ float ex2_fast(float x) {   // 2^x, one MUFU; arguments are <= 0 here, -inf -> 0
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 // D(16x8,f32) += A(16x16,bf16,row) * B(16x8,bf16,col)
 __device__ __forceinline__ void mma_bf16(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
   asm volatile(
@@ -56,7 +71,7 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-__global__ void __launch_bounds__(128) window_attention_kernel(const WinAttnParams p) {
+__global__ void __launch_bounds__(128, 6) window_attention_kernel(const WinAttnParams p) {
   __shared__ __align__(16) __nv_bfloat16 sbuf[2][3][WA_ROWS * WA_PITCH];
   __shared__ int8_t sRid[2][WA_ROWS];
 
@@ -94,17 +109,36 @@ __global__ void __launch_bounds__(128) window_attention_kernel(const WinAttnPara
   }
   const float sscale = p.scale * LOG2E;
 
+  // Loop-invariant addressing. Loads: a (window, head) is 3 matrices x N rows x 4 chunks of 16 B; chunk ids tid and
+  // tid + 128 cover rows 0..63 (rows >= N are skipped). Stores: rows r0 / r0 + 8, 4 bytes per 8-column n-tile.
+  const int lrow0 = tid >> 2, lrow1 = lrow0 + 32, lch = tid & 3;
+  const bool lv0 = lrow0 < N, lv1 = lrow1 < N;
+  const __nv_bfloat16* gsrc = p.qkv + static_cast<size_t>(lrow0) * ld + h * WA_D + lch * 8;
+  const size_t g_row32 = static_cast<size_t>(32) * ld;
+  const size_t g_win = static_cast<size_t>(N) * ld;
+  const uint32_t s_dst0 = smem_u32(&sbuf[0][0][lrow0 * WA_PITCH + lch * 8]);
+  constexpr uint32_t S_MAT = WA_ROWS * WA_PITCH * 2, S_BUF = 3 * S_MAT, S_ROW32 = 32 * WA_PITCH * 2;
   auto issue = [&](int wb, int b) {
-    // 3 matrices x N rows x 4 chunks of 16 B
-    for (int idx = tid; idx < 3 * N * 4; idx += 128) {
-      const int mat = idx / (N * 4);
-      const int rem = idx - mat * (N * 4);
-      const int row = rem >> 2, ch = rem & 3;
-      cp_async16(&sbuf[b][mat][row * WA_PITCH + ch * 8],
-                 p.qkv + (static_cast<size_t>(wb) * N + row) * ld + mat * p.C + h * WA_D + ch * 8);
+    const __nv_bfloat16* g = gsrc + static_cast<size_t>(wb) * g_win;
+    const uint32_t d = s_dst0 + static_cast<uint32_t>(b) * S_BUF;
+#pragma unroll
+    for (int mat = 0; mat < 3; ++mat) {
+      if (lv0) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d + mat * S_MAT), "l"(g + mat * p.C) : "memory");
+      if (lv1)
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d + mat * S_MAT + S_ROW32), "l"(g + mat * p.C + g_row32)
+                     : "memory");
     }
     cp_async_commit();
   };
+  __nv_bfloat16* gout = p.out + static_cast<size_t>(r0) * p.C + h * WA_D + cq;
+  const size_t o_win = static_cast<size_t>(N) * p.C;
+  const size_t o_row8 = static_cast<size_t>(8) * p.C;
+  const bool sv0 = r0 < N, sv1 = r0 + 8 < N;
+  // ldmatrix source offsets (bytes inside one matrix)
+  const uint32_t q_off = ((warp * 16 + (lane & 15)) * WA_PITCH + (lane >> 4) * 8) * 2;
+  const uint32_t k_off = (((lane & 7) + (lane >> 4) * 8) * WA_PITCH + ((lane >> 3) & 1) * 8) * 2;
+  const uint32_t v_off = (((lane & 7) + ((lane >> 3) & 1) * 8) * WA_PITCH + (lane >> 4) * 8) * 2;
+  const uint32_t s_base = smem_u32(&sbuf[0][0][0]);
 
   int wb = blockIdx.x;
   int b = 0;
@@ -117,11 +151,16 @@ __global__ void __launch_bounds__(128) window_attention_kernel(const WinAttnPara
     } else {
       cp_async_wait<0>();
     }
-    if (use_mask && tid < N) sRid[b][tid] = p.rid[(wb % p.nW) * N + tid];
-    __syncthreads();
-    const __nv_bfloat16* sQ = sbuf[b][0];
-    const __nv_bfloat16* sK = sbuf[b][1];
-    const __nv_bfloat16* sV = sbuf[b][2];
+    int differs = 0;
+    if (use_mask && tid < N) {
+      const int8_t* rw = p.rid + (wb % p.nW) * N;
+      const int8_t mine = rw[tid];
+      sRid[b][tid] = mine;
+      differs = mine != rw[0];
+    }
+    // one barrier: the tile is visible, and (masked blocks) whether this window has more than one shift region
+    const bool masked = __syncthreads_or(differs) != 0;
+    const uint32_t sQ = s_base + static_cast<uint32_t>(b) * S_BUF, sK = sQ + S_MAT, sV = sK + S_MAT;
 
     // S = Q K^T  (16 x 56 per warp)
     float s[WA_NT][4];
@@ -130,33 +169,32 @@ __global__ void __launch_bounds__(128) window_attention_kernel(const WinAttnPara
 #pragma unroll
     for (int kk = 0; kk < WA_D / 16; ++kk) {
       uint32_t a[4];
-      ldmatrix_x4(a, sQ + (warp * 16 + (lane & 15)) * WA_PITCH + kk * 16 + (lane >> 4) * 8);
+      ldmatrix_x4_s(a, sQ + q_off + kk * 32);
 #pragma unroll
       for (int jp = 0; jp < 4; ++jp) {  // key n-tile pairs (0,1) (2,3) (4,5) (6,-)
         uint32_t bb[4];
-        ldmatrix_x4(bb, sK + (jp * 16 + (lane & 7) + (lane >> 4) * 8) * WA_PITCH + kk * 16 + ((lane >> 3) & 1) * 8);
+        ldmatrix_x4_s(bb, sK + k_off + jp * (16 * WA_PITCH * 2) + kk * 32);
         mma_bf16(s[2 * jp], a, bb[0], bb[1]);
         if (jp < 3) mma_bf16(s[jp < 3 ? 2 * jp + 1 : 0], a, bb[2], bb[3]);
       }
     }
     // log2-domain logits: s*scale*log2e + bias*log2e (+ mask); row max; exp2
-    float mx[2] = {-INFINITY, -INFINITY};
-    if (use_mask) {
+#pragma unroll
+    for (int j = 0; j < WA_NT; ++j)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) s[j][e] = fmaf(s[j][e], sscale, bfr[j][e]);
+    if (masked) {   // uniform over the CTA: only the last window row / column of a shifted block get here
       const int8_t rr0 = sRid[b][r0], rr1 = sRid[b][(r0 + 8) & 63];
 #pragma unroll
       for (int j = 0; j < WA_NT; ++j) {
         const int8_t c0 = sRid[b][j * 8 + cq], c1 = sRid[b][j * 8 + cq + 1];
-        s[j][0] = fmaf(s[j][0], sscale, bfr[j][0]) + (rr0 != c0 ? -100.f * LOG2E : 0.f);
-        s[j][1] = fmaf(s[j][1], sscale, bfr[j][1]) + (rr0 != c1 ? -100.f * LOG2E : 0.f);
-        s[j][2] = fmaf(s[j][2], sscale, bfr[j][2]) + (rr1 != c0 ? -100.f * LOG2E : 0.f);
-        s[j][3] = fmaf(s[j][3], sscale, bfr[j][3]) + (rr1 != c1 ? -100.f * LOG2E : 0.f);
+        s[j][0] += (rr0 != c0 ? -100.f * LOG2E : 0.f);
+        s[j][1] += (rr0 != c1 ? -100.f * LOG2E : 0.f);
+        s[j][2] += (rr1 != c0 ? -100.f * LOG2E : 0.f);
+        s[j][3] += (rr1 != c1 ? -100.f * LOG2E : 0.f);
       }
-    } else {
-#pragma unroll
-      for (int j = 0; j < WA_NT; ++j)
-#pragma unroll
-        for (int e = 0; e < 4; ++e) s[j][e] = fmaf(s[j][e], sscale, bfr[j][e]);
     }
+    float mx[2] = {-INFINITY, -INFINITY};
 #pragma unroll
     for (int j = 0; j < WA_NT; ++j) {
       mx[0] = fmaxf(mx[0], fmaxf(s[j][0], s[j][1]));
@@ -172,7 +210,7 @@ __global__ void __launch_bounds__(128) window_attention_kernel(const WinAttnPara
     for (int j = 0; j < WA_NT; ++j) {
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
-        const float v = exp2f(s[j][e] - mx[e >> 1]);
+        const float v = ex2_fast(s[j][e] - mx[e >> 1]);
         s[j][e] = v;
         sum[e >> 1] += v;
       }
@@ -202,21 +240,17 @@ __global__ void __launch_bounds__(128) window_attention_kernel(const WinAttnPara
 #pragma unroll
       for (int np = 0; np < 2; ++np) {  // dim n-tile pairs (0,1), (2,3)
         uint32_t bb[4];
-        ldmatrix_x4_trans(bb, sV + (kk * 16 + (lane & 7) + ((lane >> 3) & 1) * 8) * WA_PITCH + np * 16 + (lane >> 4) * 8);
+        ldmatrix_x4_trans_s(bb, sV + v_off + kk * (16 * WA_PITCH * 2) + np * 32);
         mma_bf16(o[2 * np], a, bb[0], bb[1]);
         mma_bf16(o[2 * np + 1], a, bb[2], bb[3]);
       }
     }
-    const float inv0 = 1.f / sum[0], inv1 = 1.f / sum[1];
+    const float inv0 = __fdividef(1.f, sum[0]), inv1 = __fdividef(1.f, sum[1]);
+    __nv_bfloat16* go = gout + static_cast<size_t>(wb) * o_win;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      const int col = h * WA_D + j * 8 + cq;
-      if (r0 < N)
-        *reinterpret_cast<uint32_t*>(p.out + (static_cast<size_t>(wb) * N + r0) * p.C + col) =
-            pack_bf16(o[j][0] * inv0, o[j][1] * inv0);
-      if (r0 + 8 < N)
-        *reinterpret_cast<uint32_t*>(p.out + (static_cast<size_t>(wb) * N + r0 + 8) * p.C + col) =
-            pack_bf16(o[j][2] * inv1, o[j][3] * inv1);
+      if (sv0) *reinterpret_cast<uint32_t*>(go + j * 8) = pack_bf16(o[j][0] * inv0, o[j][1] * inv0);
+      if (sv1) *reinterpret_cast<uint32_t*>(go + o_row8 + j * 8) = pack_bf16(o[j][2] * inv1, o[j][3] * inv1);
     }
     __syncthreads();  // every warp is done with buffer b before the next iteration refills it
   }
@@ -379,8 +413,19 @@ cudaError_t launch_window_attention(const __nv_bfloat16* qkv, __nv_bfloat16* out
                                     cudaStream_t stream) {
   if (C != heads * WA_D || N > 49 || N < 1 || num_windows <= 0 || (C % 8) != 0) return cudaErrorInvalidValue;
   WinAttnParams p{qkv, out, bias, rid, num_windows, nW, heads, C, N, scale};
-  // persistent over windows: ~6 resident CTAs per SM in total, split across the heads (grid.y)
-  int gx = (148 * 6 + heads - 1) / heads;
+  // persistent over windows: exactly one wave of resident CTAs (a partial second wave would run alone at the end),
+  // split across the heads (grid.y)
+  static int resident = 0;   // CTAs that fit on the device at once
+  if (resident == 0) {
+    int dev = 0, sms = 148, per_sm = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, window_attention_kernel, 128, 0) != cudaSuccess || per_sm < 1)
+      per_sm = 4;
+    resident = sms * per_sm;
+  }
+  int gx = resident / heads;
+  if (gx < 1) gx = 1;
   if (gx > num_windows) gx = num_windows;
   dim3 grid(gx, heads);
   window_attention_kernel<<<grid, 128, 0, stream>>>(p);

@@ -12,8 +12,8 @@
 //     products into 96 TMEM columns;
 //   * 12 GELU warps (3 groups) drain the fc1 accumulators 64 columns at a time (tcgen05.ld -> bias -> erf-GELU ->
 //     bf16) into a double-buffered shared-memory chunk that is the A operand of the next fc2 partial product;
-//   * 4 output warps add the fc2 bias and hand 32-column slabs to TMA, which applies the residual as an fp32
-//     reduce-add into x (cp.reduce.async.bulk.tensor .add): the residual is never loaded by the SM at all.
+//   * four of the LayerNorm warps also drain the fc2 accumulator: + bias, 32-column slabs handed to TMA, which applies
+//     the residual as an fp32 reduce-add into x (cp.reduce.async.bulk.tensor .add): the SM never loads the residual.
 // Shared memory (bytes): W1 main 49152 | W1 tail 24576 | W2 73728 | A 32768 | hidden 2x16384 | out slab 16384.
 #include "mlp_fused.cuh"
 
@@ -30,11 +30,10 @@ namespace {
 constexpr int TILE_M = 128;
 constexpr int GELU_GROUPS = 3;
 constexpr int GELU_WARPS = 4 * GELU_GROUPS;   // warps 0..11
-constexpr int OUT_WARP0 = GELU_WARPS;         // warps 12..15 (warp % 4 == TMEM lane quarter)
-constexpr int LN_WARP0 = OUT_WARP0 + 4;       // warps 16..23
-constexpr int LN_WARPS = 8;
-constexpr int MMA_WARP = LN_WARP0 + LN_WARPS; // warp 24
-constexpr int THREADS = (MMA_WARP + 1) * 32;  // 800
+constexpr int LN_WARP0 = GELU_WARPS;          // warps 12..19: LayerNorm; 12..15 (warp % 4 == TMEM lane quarter) also
+constexpr int LN_WARPS = 8;                   //   drain the fc2 accumulator
+constexpr int MMA_WARP = LN_WARP0 + LN_WARPS; // warp 20
+constexpr int THREADS = (MMA_WARP + 1) * 32;  // 672
 
 constexpr int OFF_W1M = 0;
 constexpr int OFF_W1T = 49152;
@@ -85,6 +84,8 @@ swin_mlp96_fused_kernel(const __grid_constant__ CUtensorMap tmX, const Mlp96Para
   __shared__ uint64_t hid_full[2], hid_empty[2];
   __shared__ uint64_t out_full, out_empty;
   __shared__ uint32_t tmem_base_slot;
+  __shared__ uint32_t hid_written[2];   // completed writes of each hidden buffer (monotonic; see the GELU groups)
+  __shared__ __align__(16) float sb1[MLP96_H];
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -103,13 +104,15 @@ swin_mlp96_fused_kernel(const __grid_constant__ CUtensorMap tmX, const Mlp96Para
     }
     mbar_init(&out_full, 1);
     mbar_init(&out_empty, 128);
+    hid_written[0] = hid_written[1] = 0;
     fence_barrier_init();
   }
   if (warp == MMA_WARP) {
     tmem_alloc(&tmem_base_slot, TM_COLS);
     tmem_relinquish();
   }
-  if (warp == OUT_WARP0 && lane == 0) tma_prefetch_desc(&tmX);
+  if (warp == LN_WARP0 && lane == 0) tma_prefetch_desc(&tmX);
+  for (int idx = threadIdx.x; idx < MLP96_H; idx += THREADS) sb1[idx] = p.b1[idx];
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -185,11 +188,12 @@ swin_mlp96_fused_kernel(const __grid_constant__ CUtensorMap tmX, const Mlp96Para
       }
     }
   } else if (warp >= LN_WARP0) {
-    // ------------------------------------------------------------------ LayerNorm -> bf16 A tile
+    // ------------------------------------------------------------------ LayerNorm -> bf16 A tile  (+ output drain)
     const int t = threadIdx.x - LN_WARP0 * 32;   // 0..255
     const int l8 = t & 7;                        // lane within the 8-lane row team
-    const int rg = t >> 3;                       // 0..31: rows rg, rg+32, rg+64, rg+96
-    for (int i = 0; i < n_local; ++i) {
+    const int tt = t >> 3;                       // team 0..31 -> rows rg + 32q; the four teams of a warp sit on rows
+    const int rg = 8 * (tt >> 3) + ((tt & 1) << 2) + ((tt >> 1) & 3);   // whose swizzle phases spread over all banks
+    auto layer_norm_tile = [&](int i) {
       const int m0 = (static_cast<int>(blockIdx.x) + i * static_cast<int>(gridDim.x)) * TILE_M;
       float4 xv[4][3];
 #pragma unroll
@@ -245,15 +249,15 @@ swin_mlp96_fused_kernel(const __grid_constant__ CUtensorMap tmX, const Mlp96Para
       }
       fence_proxy_async_smem();
       mbar_arrive(&a_full);
-    }
-  } else if (warp >= OUT_WARP0) {
-    // ------------------------------------------------------------------ fc2 accumulator -> + bias -> reduce-add into x
+    };
+    // fc2 accumulator -> + bias -> 32-column slabs -> TMA reduce-add into x (warps LN_WARP0 .. LN_WARP0 + 3)
+    const bool out_warp = warp < LN_WARP0 + 4;
     const int quarter = warp & 3;
     const int row = quarter * 32 + lane;
     const int sw = row & 7;
-    const bool elected = threadIdx.x == OUT_WARP0 * 32;
+    const bool elected = threadIdx.x == LN_WARP0 * 32;
     uint8_t* my_out = smem + OFF_IO + row * 128;
-    for (int i = 0; i < n_local; ++i) {
+    auto drain_tile = [&](int i) {
       const int m0 = (static_cast<int>(blockIdx.x) + i * static_cast<int>(gridDim.x)) * TILE_M;
       mbar_wait(&out_full, i & 1u, 23);
       tc_fence_after();
@@ -287,6 +291,11 @@ swin_mlp96_fused_kernel(const __grid_constant__ CUtensorMap tmX, const Mlp96Para
           tma_store_commit();
         }
       }
+    };
+    layer_norm_tile(0);
+    for (int i = 0; i < n_local; ++i) {
+      if (i + 1 < n_local) layer_norm_tile(i + 1);
+      if (out_warp) drain_tile(i);
     }
     if (elected) tma_store_wait_all();
   } else {
@@ -301,40 +310,57 @@ swin_mlp96_fused_kernel(const __grid_constant__ CUtensorMap tmX, const Mlp96Para
         const int c = group + 3 * hh;                       // chunk of this tile: hidden columns [64c, 64c + 64)
         const uint32_t n = 6u * static_cast<uint32_t>(i) + static_cast<uint32_t>(c);
         const int buf = n & 1;
+        uint8_t* my_hid = smem + OFF_HID + buf * 16384 + row * 128;
+        const float* bias = sb1 + 64 * c;
         mbar_wait(&d_full[hh], i & 1u, 24);
         tc_fence_after();
         const uint32_t t_col = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) +
                                static_cast<uint32_t>((hh ? TM_D1 : TM_D0) + group * 64);
-        const float* bias = p.b1 + 64 * c;
-        uint32_t pk[32];
-        {
-          uint32_t v[32];
-          tmem_ld_32x32b_x32(t_col, v);
-          tmem_ld_wait();
+        uint32_t v[32];
+        uint32_t pk[16];
+        tmem_ld_32x32b_x32(t_col, v);
+        tmem_ld_wait();
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias) + j);
-            pk[2 * j] = pack_bf16(gelu_erf(__uint_as_float(v[4 * j]) + b4.x), gelu_erf(__uint_as_float(v[4 * j + 1]) + b4.y));
-            pk[2 * j + 1] = pack_bf16(gelu_erf(__uint_as_float(v[4 * j + 2]) + b4.z), gelu_erf(__uint_as_float(v[4 * j + 3]) + b4.w));
-          }
-          tmem_ld_32x32b_x32(t_col + 32u, v);
-          tmem_ld_wait();
-          tc_fence_before();
-          mbar_arrive(&d_empty[hh]);                        // this thread no longer needs the accumulator half
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + 32) + j);
-            pk[16 + 2 * j] = pack_bf16(gelu_erf(__uint_as_float(v[4 * j]) + b4.x), gelu_erf(__uint_as_float(v[4 * j + 1]) + b4.y));
-            pk[16 + 2 * j + 1] = pack_bf16(gelu_erf(__uint_as_float(v[4 * j + 2]) + b4.z), gelu_erf(__uint_as_float(v[4 * j + 3]) + b4.w));
+        for (int j = 0; j < 8; ++j) {
+          const float4 b4 = *reinterpret_cast<const float4*>(bias + 4 * j);
+          pk[2 * j] = pack_bf16(gelu_erf(__uint_as_float(v[4 * j]) + b4.x), gelu_erf(__uint_as_float(v[4 * j + 1]) + b4.y));
+          pk[2 * j + 1] = pack_bf16(gelu_erf(__uint_as_float(v[4 * j + 2]) + b4.z), gelu_erf(__uint_as_float(v[4 * j + 3]) + b4.w));
+        }
+        tmem_ld_32x32b_x32(t_col + 32u, v);
+        // Use k of this buffer may be written once fc2 has consumed use k-1. The three groups take turns on the two
+        // buffers, so a parity wait alone could be satisfied by a phase two uses back: first make sure use k-1 has
+        // been WRITTEN (monotonic counter), which pins the barrier to phase k-1 or k, then wait for phase k-1.
+        const uint32_t use = n >> 1;
+        if (use > 0) {
+          uint32_t spins = 0;
+          while (*reinterpret_cast<volatile uint32_t*>(&hid_written[buf]) < use) {
+            if (((++spins) & 0x3FFF) == 0 &&
+                (*reinterpret_cast<volatile unsigned int*>(&g_mbar_timeout) != 0 || spins > (1u << 24))) {
+              atomicCAS(&g_mbar_timeout, 0u, 0x80000000u | (26u << 24) | ((blockIdx.x & 0xFFF) << 12) | (threadIdx.x & 0xFFF));
+              break;
+            }
           }
         }
-        mbar_wait(&hid_empty[buf], ((n >> 1) & 1u) ^ 1u, 25);   // fc2 has consumed the previous use of this buffer
-        uint8_t* my_hid = smem + OFF_HID + buf * 16384 + row * 128;
+        mbar_wait(&hid_empty[buf], (use & 1u) ^ 1u, 25);
 #pragma unroll
-        for (int j = 0; j < 8; ++j)
+        for (int j = 0; j < 4; ++j)
           *reinterpret_cast<uint4*>(my_hid + ((j ^ sw) << 4)) = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+        tmem_ld_wait();
+        tc_fence_before();
+        mbar_arrive(&d_empty[hh]);                          // this thread no longer needs the accumulator half
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float4 b4 = *reinterpret_cast<const float4*>(bias + 32 + 4 * j);
+          pk[2 * j] = pack_bf16(gelu_erf(__uint_as_float(v[4 * j]) + b4.x), gelu_erf(__uint_as_float(v[4 * j + 1]) + b4.y));
+          pk[2 * j + 1] = pack_bf16(gelu_erf(__uint_as_float(v[4 * j + 2]) + b4.z), gelu_erf(__uint_as_float(v[4 * j + 3]) + b4.w));
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          *reinterpret_cast<uint4*>(my_hid + (((4 + j) ^ sw) << 4)) = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
         fence_proxy_async_smem();
         mbar_arrive(&hid_full[buf]);
+        named_bar_sync(2 + group, 128);                     // every thread of the group has written this use
+        if ((threadIdx.x & 127) == 0) *reinterpret_cast<volatile uint32_t*>(&hid_written[buf]) = use + 1;
       }
     }
   }

@@ -188,18 +188,20 @@ __host__ __device__ __forceinline__ uint32_t make_idesc_bf16(int m, int n) {
 
 // ---------------------------------------------------------------- misc
 // Exact-erf GELU (nn.GELU(), F.gelu, modules/Transformer.py:119-124): 0.5*x*(1+erf(x/sqrt2)).
-// erfc(z) = 2^P(z) on z = |x|/sqrt2 in [0, 4.2] with a degree-5 polynomial fitted to log2(erfc) (max |gelu error|
-// 1.4e-6 in fp32 over the whole real line, i.e. erff-grade), so one GELU costs 6 FMA + one MUFU.EX2 instead of the
-// ~30-instruction erff or a reciprocal + exp. The negative branch uses 0.5*x*erfc(z) directly: no cancellation.
+// 0.5*erfc(z) = 2^P(z) on z = |x|/sqrt2 with a degree-5 polynomial fitted to log2(erfc) on [0, 4.2] (the 0.5 is folded
+// into the constant term; max |gelu error| 1.4e-6 in fp32 over the whole real line, i.e. erff-grade). Beyond the fit
+// range P keeps decreasing, so 2^P -> 0 without a clamp. gelu = relu(x) - |x| * 2^P: 6 FMA + 1 FMUL + 1 FMNMX + one
+// MUFU.EX2 instead of the ~30-instruction erff; the negative branch has no cancellation.
 __device__ __forceinline__ float gelu_erf(float x) {
-  const float z = fminf(fabsf(x) * 0.70710678118654752f, 4.2f);
+  const float z = fabsf(x) * 0.70710678118654752f;
   float p = fmaf(z, -2.98332428e-03f, 2.97336457e-02f);
   p = fmaf(z, p, -1.48837507e-01f);
   p = fmaf(z, p, -9.18433869e-01f);
   p = fmaf(z, p, -1.62789775e+00f);
-  p = fmaf(z, p, -2.71726947e-07f);
-  const float h = 0.5f * x * exp2f(p);          // 0.5 * x * erfc(|x|/sqrt2), same sign as x
-  return fmaxf(x, 0.0f) - fabsf(h);
+  p = fmaf(z, p, -1.0f - 2.71726947e-07f);
+  float e;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(p));
+  return fmaf(-fabsf(x), e, fmaxf(x, 0.0f));
 }
 
 __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
