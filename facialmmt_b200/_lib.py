@@ -58,6 +58,8 @@ SIGNATURES = {
     "fmmt_set_profile": (c_int, [c_void_p, c_int]),
     "fmmt_profile_read": (c_int64, [c_void_p, c_void_p, c_int64]),
     "fmmt_debug_timeout": (ctypes.c_uint32, [c_int]),
+    "fmmt_debug_mma_cycles": (c_double, [c_int, c_int]),
+    "fmmt_debug_feed": (c_int, [c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "fmmt_flops": (c_double, [c_void_p, c_int]),
     "fmmt_device_bytes": (c_int64, [c_void_p]),
     "fmmt_op_gemm": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int, c_void_p, c_int,

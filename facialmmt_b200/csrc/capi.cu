@@ -123,6 +123,12 @@ FMMT_API uint32_t fmmt_debug_timeout(int reset) {
   return a != 0 ? a : b;
 }
 
+FMMT_API double fmmt_debug_mma_cycles(int n, int iters) { return mma_rate_probe(n, iters); }
+
+FMMT_API int fmmt_debug_feed(int iters, int nstage, int box_rows, int mode, int grid, double* out2) {
+  return feed_probe(iters, nstage, box_rows, mode, grid, out2);
+}
+
 FMMT_API double fmmt_flops(fmmt_handle* h, int reset) { return h ? h->eng->flops(reset != 0) : 0.0; }
 FMMT_API int64_t fmmt_device_bytes(fmmt_handle* h) { return h ? h->eng->device_bytes() : 0; }
 
@@ -140,8 +146,15 @@ FMMT_API int fmmt_op_gemm(const void* A_bf16, int lda, const void* W_bf16, int l
   a.out_f32 = out_f32; a.ldo32 = ldo32;
   a.out_bf16 = static_cast<__nv_bfloat16*>(out_bf16); a.ldo16 = ldo16;
   a.row_map = row_map; a.map_period = map_period;
-  a.block_n = block_n < 0 ? (block_n == -1 ? 0 : -block_n) : block_n;
-  a.force_generic = block_n < 0;
+  // block_n: 0 auto; > 0 fixed tile width (single-CTA kernels); < 0 register-path epilogue (-1 auto, else -block_n);
+  // >= 1000 CTA-pair kernel (1000 auto, else block_n - 1000); 999 = single-CTA kernels only
+  if (block_n >= 1000) { a.two_cta = 1; a.block_n = block_n - 1000; }
+  else if (block_n == 999) { a.two_cta = -1; a.block_n = 0; }
+  else {
+    a.two_cta = block_n != 0 ? -1 : 0;
+    a.block_n = block_n < 0 ? (block_n == -1 ? 0 : -block_n) : block_n;
+    a.force_generic = block_n < 0;
+  }
   count_launch();
   return check_cuda(launch_gemm(a, S(stream)), "fmmt_op_gemm");
 }

@@ -10,6 +10,8 @@
 #include "ptx.cuh"
 
 #include <cmath>
+#include <cstdio>
+#include <cstdlib>
 #include <mutex>
 
 namespace fmmt {
@@ -29,7 +31,7 @@ constexpr int MAX_STAGES = 8;
 constexpr int TMEM_COLS = 512;       // two accumulator stages of up to 256 fp32 columns
 constexpr int ACC_STRIDE = 256;
 constexpr int A_TILE_BYTES = BM * BK * 2;  // 16 KB
-constexpr int SMEM_BUDGET = 220 * 1024;
+constexpr int SMEM_BUDGET = 225 * 1024;   // + 1 KB alignment slack + static barriers <= 227 KB
 
 struct GemmKernelParams {
   int M, N, K;
@@ -294,6 +296,7 @@ struct FastParams {
   int slab_cols;
   int groups;      // active epilogue groups (2 or 4) == staging slabs == residual ring slots: compute-heavy GEMMs
                    // (large K) give the shared memory to the A/B pipeline instead of the epilogue rings
+  int kbs;         // pair kernel: 64-column k-blocks per pipeline stage (1 or 2); stage_bytes covers all of them
 };
 
 template <int ACT>
@@ -320,7 +323,7 @@ __device__ __forceinline__ uint32_t pack_bf16_bits(uint32_t a, uint32_t b) {
   return pack_bf16(__uint_as_float(a), __uint_as_float(b));
 }
 
-template <int ACT>
+template <int ACT, int KBS>
 __global__ void __launch_bounds__(FAST_THREADS, 1)
 gemm_bf16_tcgen05_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                              const __grid_constant__ CUtensorMap tmRes, const __grid_constant__ CUtensorMap tmOut,
@@ -382,13 +385,18 @@ gemm_bf16_tcgen05_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __gr
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const int m0 = (tile / p.n_tiles) * BM;
         const int n0 = (tile % p.n_tiles) * p.block_n;
-        for (int kb = 0; kb < p.num_kb; ++kb) {
+        for (int kb = 0; kb < p.num_kb; kb += KBS) {
           mbar_wait(&empty_bar[stage], phase ^ 1u, 1);
           uint8_t* sa = pipe_gen + stage * p.stage_bytes;
-          uint8_t* sb = sa + A_TILE_BYTES;
+          uint8_t* sb = sa + KBS * A_TILE_BYTES;
           mbar_arrive_expect_tx(&full_bar[stage], static_cast<uint32_t>(p.stage_bytes));
-          tma_load_2d(sa, &tmA, &full_bar[stage], kb * BK, m0);
-          tma_load_2d(sb, &tmB, &full_bar[stage], kb * BK, n0);
+          if (KBS > 1) {   // KBS k-blocks per instruction (3-D tensor maps; k-blocks past K are zero-filled)
+            tma_load_3d(sa, &tmA, &full_bar[stage], 0, m0, kb);
+            tma_load_3d(sb, &tmB, &full_bar[stage], 0, n0, kb);
+          } else {
+            tma_load_2d(sa, &tmA, &full_bar[stage], kb * BK, m0);
+            tma_load_2d(sb, &tmB, &full_bar[stage], kb * BK, n0);
+          }
           if (++stage == p.num_stages) { stage = 0; phase ^= 1u; }
         }
       }
@@ -404,17 +412,21 @@ gemm_bf16_tcgen05_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __gr
         mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1u, 2);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * ACC_STRIDE);
-        for (int kb = 0; kb < p.num_kb; ++kb) {
+        for (int kb = 0; kb < p.num_kb; kb += KBS) {
           mbar_wait(&full_bar[stage], phase, 3);
           tc_fence_after();
           const uint32_t sa = pipe_base + stage * p.stage_bytes;
-          const uint64_t adesc = make_smem_desc_sw128(sa);
-          const uint64_t bdesc = make_smem_desc_sw128(sa + A_TILE_BYTES);
-          int ksteps = (p.K - kb * BK + UMMA_K - 1) / UMMA_K;
-          if (ksteps > BK / UMMA_K) ksteps = BK / UMMA_K;
-          for (int k = 0; k < ksteps; ++k)
-            umma_bf16(d_tmem, adesc + static_cast<uint64_t>(2 * k), bdesc + static_cast<uint64_t>(2 * k), idesc,
-                      (kb | k) != 0 ? 1u : 0u);
+          const uint32_t sb = sa + KBS * A_TILE_BYTES;
+          #pragma unroll
+          for (int j = 0; j < KBS; ++j) {
+            const uint64_t adesc = make_smem_desc_sw128(sa + j * A_TILE_BYTES);
+            const uint64_t bdesc = make_smem_desc_sw128(sb + j * (p.block_n * BK * 2));
+            int ksteps = (p.K - (kb + j) * BK + UMMA_K - 1) / UMMA_K;
+            if (ksteps > BK / UMMA_K) ksteps = BK / UMMA_K;
+            for (int k = 0; k < ksteps; ++k)
+              umma_bf16(d_tmem, adesc + static_cast<uint64_t>(2 * k), bdesc + static_cast<uint64_t>(2 * k), idesc,
+                        ((kb + j) | k) != 0 ? 1u : 0u);
+          }
           umma_commit(&empty_bar[stage]);
           if (++stage == p.num_stages) { stage = 0; phase ^= 1u; }
         }
@@ -542,6 +554,354 @@ gemm_bf16_tcgen05_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __gr
   }
 }
 
+
+// ====================================================================================================================
+// CTA-pair variant (tcgen05 cta_group::2): a cluster of two CTAs on one TPC computes a 256 x block_n tile. Each CTA
+// loads ITS 128 rows of A and HALF of the B rows (block_n / 2) per k-block, so the shared-memory ingest per SM per
+// FLOP drops by (128 + bn) / (128 + bn / 2) against the single-CTA kernel (1.5x at bn = 256) - the quantity that bounds
+// the K = 384 .. 4096 GEMMs of this path (operand feed from L2, see pick_block_n). The leader CTA's MMA thread issues
+// M = 256 instructions that read both CTAs' shared memory and write both CTAs' TMEM; every CTA runs its own TMA
+// producer, residual producer and epilogue for its 128 rows. Barriers:
+//   full_bar[s]   (leader's copy)  1 arrival (leader's producer) + the bytes of both CTAs' loads
+//   empty_bar[s]  (each CTA)       1 arrival by tcgen05.commit multicast to the pair
+//   tmem_full[a]  (each CTA)       1 arrival by commit multicast;  tmem_empty[a] (leader's copy) all epilogue threads
+//                                  of BOTH CTAs (remote arrive through the shared::cluster window)
+template <int ACT>
+__global__ void __launch_bounds__(FAST_THREADS, 1)
+gemm_bf16_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                              const __grid_constant__ CUtensorMap tmRes, const __grid_constant__ CUtensorMap tmOut,
+                              const FastParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ uint64_t full_bar[MAX_STAGES];
+  __shared__ uint64_t empty_bar[MAX_STAGES];
+  __shared__ uint64_t tmem_full_bar[2];
+  __shared__ uint64_t tmem_empty_bar[2];
+  __shared__ uint64_t res_full_bar[RES_SLOTS];
+  __shared__ uint64_t res_empty_bar[RES_SLOTS];
+  __shared__ uint32_t tmem_base_slot;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  uint8_t* out_ring = smem_gen;
+  uint8_t* res_ring = out_ring + p.groups * SLAB_BYTES;
+  const int ring_bytes = (p.has_res ? 2 : 1) * p.groups * SLAB_BYTES;
+  uint8_t* pipe_gen = smem_gen + ring_bytes;
+  const uint32_t pipe_base = smem_base + ring_bytes;
+  const int half_n = p.block_n >> 1;
+  const int sub_bytes = A_TILE_BYTES + half_n * (BK * 2);   // one k-block of this CTA's operands
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < p.num_stages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tmem_full_bar[s], 1);
+      mbar_init(&tmem_empty_bar[s], 2 * FAST_EPI_WARPS);   // one (remote) arrival per epilogue warp of either CTA
+    }
+    for (int s = 0; s < RES_SLOTS; ++s) {
+      mbar_init(&res_full_bar[s], 1);
+      mbar_init(&res_empty_bar[s], 128);
+    }
+    fence_barrier_init();
+  }
+  if (warp == FAST_PRODUCER_WARP && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    tma_prefetch_desc(&tmOut);
+    if (p.has_res) tma_prefetch_desc(&tmRes);
+  }
+  if (warp == FAST_MMA_WARP) {
+    tmem_alloc_pair(&tmem_base_slot, TMEM_COLS);
+    tmem_relinquish_pair();
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_arrive_release();      // the peer's barriers are initialised and its TMEM is allocated before anyone signals
+  cluster_wait_acquire();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_slot;
+  const int num_tiles = p.m_tiles * p.n_tiles;
+  const int pair_id = static_cast<int>(blockIdx.x >> 1);
+  const int num_pairs = static_cast<int>(gridDim.x >> 1);
+
+  if (warp == FAST_PRODUCER_WARP) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = pair_id; tile < num_tiles; tile += num_pairs) {
+        const int m0 = (tile / p.n_tiles) * (2 * BM) + static_cast<int>(rank) * BM;
+        const int nb0 = (tile % p.n_tiles) * p.block_n + static_cast<int>(rank) * half_n;
+        for (int kb = 0; kb < p.num_kb; kb += p.kbs) {
+          mbar_wait(&empty_bar[stage], phase ^ 1u, 1);
+          uint8_t* sa = pipe_gen + stage * p.stage_bytes;
+          const uint32_t lead_full = mapa_u32(smem_u32(&full_bar[stage]), 0);
+          // one arrival (the leader's) + the bytes of both CTAs: the peer only refills a slot after the commit that
+          // followed the leader's wait on the slot's previous phase, so its bytes always land in the right phase
+          if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2u * static_cast<uint32_t>(p.stage_bytes));
+          if (p.kbs > 1) {   // one instruction per operand: kbs k-blocks (past K: zero-filled, skipped by the MMA thread)
+            tma_load_3d_pair(sa, &tmA, lead_full, 0, m0, kb);
+            tma_load_3d_pair(sa + p.kbs * A_TILE_BYTES, &tmB, lead_full, 0, nb0, kb);
+          } else {
+            tma_load_2d_pair(sa, &tmA, lead_full, kb * BK, m0);
+            tma_load_2d_pair(sa + A_TILE_BYTES, &tmB, lead_full, kb * BK, nb0);
+          }
+          if (++stage == p.num_stages) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == FAST_MMA_WARP) {
+    if (lane == 0 && leader) {
+      const uint32_t idesc = make_idesc_bf16(2 * BM, p.block_n);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = pair_id; tile < num_tiles; tile += num_pairs) {
+        mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1u, 2);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * ACC_STRIDE);
+        for (int kb = 0; kb < p.num_kb; kb += p.kbs) {
+          mbar_wait(&full_bar[stage], phase, 3);
+          tc_fence_after();
+          const uint32_t sa = pipe_base + stage * p.stage_bytes;
+          const uint32_t sb = sa + p.kbs * A_TILE_BYTES;
+          for (int j = 0; j < p.kbs; ++j) {
+            const uint64_t adesc = make_smem_desc_sw128(sa + j * A_TILE_BYTES);
+            const uint64_t bdesc = make_smem_desc_sw128(sb + j * (sub_bytes - A_TILE_BYTES));
+            int ksteps = (p.K - (kb + j) * BK + UMMA_K - 1) / UMMA_K;
+            if (ksteps > BK / UMMA_K) ksteps = BK / UMMA_K;
+            for (int k = 0; k < ksteps; ++k)
+              umma_bf16_pair(d_tmem, adesc + static_cast<uint64_t>(2 * k), bdesc + static_cast<uint64_t>(2 * k), idesc,
+                             ((kb + j) | k) != 0 ? 1u : 0u);
+          }
+          umma_commit_pair(&empty_bar[stage]);
+          if (++stage == p.num_stages) { stage = 0; phase ^= 1u; }
+        }
+        umma_commit_pair(&tmem_full_bar[acc]);
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1u;
+      }
+    }
+  } else if (warp == FAST_RES_WARP) {
+    if (lane == 0 && p.has_res) {
+      uint32_t cnt = 0;
+      for (int tile = pair_id; tile < num_tiles; tile += num_pairs) {
+        const int m0 = (tile / p.n_tiles) * (2 * BM) + static_cast<int>(rank) * BM;
+        const int n0 = (tile % p.n_tiles) * p.block_n;
+        int ncols = p.N - n0;
+        if (ncols > p.block_n) ncols = p.block_n;
+        const int nsl = (ncols + p.slab_cols - 1) / p.slab_cols;
+        for (int s = 0; s < nsl; ++s, ++cnt) {
+          const int slot = cnt % p.groups;
+          const uint32_t ph = (cnt / p.groups) & 1u;
+          mbar_wait(&res_empty_bar[slot], ph ^ 1u, 4);
+          mbar_arrive_expect_tx(&res_full_bar[slot], SLAB_BYTES);
+          tma_load_2d(res_ring + slot * SLAB_BYTES, &tmRes, &res_full_bar[slot], n0 + s * p.slab_cols, m0);
+        }
+      }
+    }
+  } else {
+    const int group = warp >> 2;
+    const int quarter = warp & 3;
+    const int row = quarter * 32 + lane;
+    const int sw = row & 7;
+    const bool elected = (threadIdx.x & 127) == 0;
+    uint8_t* out_slot = out_ring + group * SLAB_BYTES;
+    uint8_t* my_out = out_slot + row * 128;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    uint32_t res_base = 0;
+    for (int tile = pair_id; tile < num_tiles; tile += num_pairs) {
+      const int m0 = (tile / p.n_tiles) * (2 * BM) + static_cast<int>(rank) * BM;
+      const int n0 = (tile % p.n_tiles) * p.block_n;
+      int ncols = p.N - n0;
+      if (ncols > p.block_n) ncols = p.block_n;
+      const int nsl = (ncols + p.slab_cols - 1) / p.slab_cols;
+      mbar_wait(&tmem_full_bar[acc], acc_phase, 5);
+      tc_fence_after();
+      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) +
+                             static_cast<uint32_t>(acc * ACC_STRIDE);
+      const uint32_t ng = static_cast<uint32_t>(p.groups);
+      int s_first = nsl;
+      if (group < p.groups) s_first = static_cast<int>((static_cast<uint32_t>(group) + ng - res_base % ng) % ng);
+      for (int s = s_first; s < nsl; s += p.groups) {
+        const int gc0 = n0 + s * p.slab_cols;
+        if (p.out_bf16) {
+          uint32_t v[32];
+          tmem_ld_32x32b_x32(t_row + static_cast<uint32_t>(s * 64), v);
+          tmem_ld_wait();
+          epi_math32<ACT>(v, p.bias, gc0, p.N, p.act);
+          if (elected) tma_store_wait_read<0>();
+          named_bar_sync(1 + group, 128);
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            *reinterpret_cast<uint4*>(my_out + ((j ^ sw) << 4)) =
+                make_uint4(pack_bf16_bits(v[8 * j], v[8 * j + 1]), pack_bf16_bits(v[8 * j + 2], v[8 * j + 3]),
+                           pack_bf16_bits(v[8 * j + 4], v[8 * j + 5]), pack_bf16_bits(v[8 * j + 6], v[8 * j + 7]));
+          tmem_ld_32x32b_x32(t_row + static_cast<uint32_t>(s * 64 + 32), v);
+          tmem_ld_wait();
+          epi_math32<ACT>(v, p.bias, gc0 + 32, p.N, p.act);
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            *reinterpret_cast<uint4*>(my_out + (((4 + j) ^ sw) << 4)) =
+                make_uint4(pack_bf16_bits(v[8 * j], v[8 * j + 1]), pack_bf16_bits(v[8 * j + 2], v[8 * j + 3]),
+                           pack_bf16_bits(v[8 * j + 4], v[8 * j + 5]), pack_bf16_bits(v[8 * j + 6], v[8 * j + 7]));
+        } else {
+          uint32_t v[32];
+          tmem_ld_32x32b_x32(t_row + static_cast<uint32_t>(s * 32), v);
+          tmem_ld_wait();
+          epi_math32<ACT>(v, p.bias, gc0, p.N, p.act);
+          if (p.has_res) {
+            const uint32_t cnt = res_base + static_cast<uint32_t>(s);
+            const int slot = cnt % p.groups;
+            mbar_wait(&res_full_bar[slot], (cnt / p.groups) & 1u, 6);
+            const uint8_t* my_res = res_ring + slot * SLAB_BYTES + row * 128;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float4 r = *reinterpret_cast<const float4*>(my_res + ((j ^ sw) << 4));
+              v[4 * j] = __float_as_uint(__uint_as_float(v[4 * j]) + r.x);
+              v[4 * j + 1] = __float_as_uint(__uint_as_float(v[4 * j + 1]) + r.y);
+              v[4 * j + 2] = __float_as_uint(__uint_as_float(v[4 * j + 2]) + r.z);
+              v[4 * j + 3] = __float_as_uint(__uint_as_float(v[4 * j + 3]) + r.w);
+            }
+            mbar_arrive(&res_empty_bar[slot]);
+          }
+          if (elected) tma_store_wait_read<0>();
+          named_bar_sync(1 + group, 128);
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            *reinterpret_cast<uint4*>(my_out + ((j ^ sw) << 4)) = make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        }
+        fence_proxy_async_smem();
+        named_bar_sync(1 + group, 128);
+        if (elected) {
+          tma_store_2d(&tmOut, out_slot, gc0, m0);
+          tma_store_commit();
+        }
+      }
+      res_base += static_cast<uint32_t>(nsl);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(&tmem_empty_bar[acc]), 0));   // the leader's MMA thread waits
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1u;
+    }
+    if (elected) tma_store_wait_all();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  cluster_arrive_release();      // neither CTA may exit (or free TMEM) while the pair's MMAs / remote arrives are in flight
+  cluster_wait_acquire();
+  if (warp == FAST_MMA_WARP) {
+    tc_fence_after();
+    tmem_dealloc_pair(tmem_base, TMEM_COLS);
+  }
+}
+
+
+// ---------------------------------------------------------------- tensor-pipe probe (test/bench only)
+// One CTA per SM issues `iters` x 4 MMAs (M = 128, N = n, K = 16 each) on the same shared-memory tiles, with no TMA
+// traffic at all, and reports the cycles of the slowest CTA: the MMA issue/execute floor of this part.
+__global__ void __launch_bounds__(128, 1) mma_rate_probe_kernel(int n, int iters, long long* cycles_out) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ uint64_t done_bar;
+  __shared__ uint32_t tmem_base_slot;
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + (smem_base - smem_u32(smem_raw));
+  for (int i = threadIdx.x; i < (A_TILE_BYTES + 256 * 128) / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem)[i] = 0x3c003c00u;
+  if (threadIdx.x == 0) { mbar_init(&done_bar, 1); fence_barrier_init(); }
+  if (threadIdx.x < 32) { tmem_alloc(&tmem_base_slot, TMEM_COLS); tmem_relinquish(); }
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_slot;
+  if (threadIdx.x == 0) {
+    const uint32_t idesc = make_idesc_bf16(BM, n);
+    const uint64_t adesc = make_smem_desc_sw128(smem_base);
+    const uint64_t bdesc = make_smem_desc_sw128(smem_base + A_TILE_BYTES);
+    const long long t0 = clock64();
+    for (int it = 0; it < iters; ++it)
+      for (int k = 0; k < 4; ++k)
+        umma_bf16(tmem_base + static_cast<uint32_t>((it & 1) * ACC_STRIDE), adesc + static_cast<uint64_t>(2 * k),
+                  bdesc + static_cast<uint64_t>(2 * k), idesc, (it | k) > 1 ? 1u : 0u);
+    umma_commit(&done_bar);
+    mbar_wait(&done_bar, 0, 7);
+    const long long t1 = clock64();
+    atomicMax(reinterpret_cast<unsigned long long*>(cycles_out), static_cast<unsigned long long>(t1 - t0));
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (threadIdx.x < 32) { tc_fence_after(); tmem_dealloc(tmem_base, TMEM_COLS); }
+}
+
+
+// Feed probe (bench only): every CTA streams `iters` boxes of 64 x box_rows bf16 (SWIZZLE_128B) from an L2-resident
+// matrix through `nstage` shared-memory slots with TMA; mode 1 additionally keeps the tensor pipe busy with N = 256
+// MMAs on two other resident tiles. Reports max cycles over CTAs for the loads (slot 0) and the MMAs (slot 1).
+__global__ void __launch_bounds__(128, 1)
+feed_probe_kernel(const __grid_constant__ CUtensorMap tm, int iters, int nstage, int box_rows, int rows_total, int mode,
+                  long long* cycles_out) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ uint64_t full[MAX_STAGES];
+  __shared__ uint64_t done_bar;
+  __shared__ uint32_t tmem_base_slot;
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + (smem_base - smem_u32(smem_raw));
+  const int box_bytes = box_rows * 128;
+  uint8_t* mma_tiles = smem + nstage * box_bytes;   // A tile + 256-row B tile
+  for (int i = threadIdx.x; i < (A_TILE_BYTES + 256 * 128) / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(mma_tiles)[i] = 0x3c003c00u;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < nstage; ++s) mbar_init(&full[s], 1);
+    mbar_init(&done_bar, 1);
+    fence_barrier_init();
+  }
+  if (threadIdx.x < 32) { tmem_alloc(&tmem_base_slot, TMEM_COLS); tmem_relinquish(); }
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_slot;
+  if (threadIdx.x == 0) {
+    const int nblk = rows_total / box_rows;
+    int blk = (blockIdx.x * 37) % nblk;
+    const long long t0 = clock64();
+    for (int it = 0; it < iters + nstage; ++it) {
+      const int s = it % nstage;
+      if (it >= nstage) mbar_wait(&full[s], ((it / nstage) - 1) & 1u, 8);
+      if (it < iters) {
+        mbar_arrive_expect_tx(&full[s], box_bytes);
+        tma_load_2d(smem + s * box_bytes, &tm, &full[s], 0, blk * box_rows);
+        blk = blk + 1 == nblk ? 0 : blk + 1;
+      }
+    }
+    const long long t1 = clock64();
+    atomicMax(reinterpret_cast<unsigned long long*>(cycles_out), static_cast<unsigned long long>(t1 - t0));
+  } else if (threadIdx.x == 32 && mode == 1) {
+    const uint32_t idesc = make_idesc_bf16(BM, 256);
+    const uint64_t adesc = make_smem_desc_sw128(smem_base + nstage * box_bytes);
+    const uint64_t bdesc = make_smem_desc_sw128(smem_base + nstage * box_bytes + A_TILE_BYTES);
+    const int n_mma = iters * box_rows / 96;   // MMA work in proportion to a 128 x 256 tile's feed (384 rows per 4 MMAs)
+    const long long t0 = clock64();
+    for (int it = 0; it < n_mma; ++it)
+      umma_bf16(tmem_base + static_cast<uint32_t>(((it >> 2) & 1) * ACC_STRIDE), adesc + static_cast<uint64_t>(2 * (it & 3)),
+                bdesc + static_cast<uint64_t>(2 * (it & 3)), idesc, it > 7 ? 1u : 0u);
+    umma_commit(&done_bar);
+    mbar_wait(&done_bar, 0, 9);
+    const long long t1 = clock64();
+    atomicMax(reinterpret_cast<unsigned long long*>(cycles_out + 1), static_cast<unsigned long long>(t1 - t0));
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (threadIdx.x < 32) { tc_fence_after(); tmem_dealloc(tmem_base, TMEM_COLS); }
+}
+
 // ---------------------------------------------------------------- host side
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                     const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -575,6 +935,23 @@ bool make_tmap(CUtensorMap* tm, const void* base, CUtensorMapDataType dt, int es
   return r == CUDA_SUCCESS;
 }
 
+// 3-D view of a K-major bf16 matrix whose K is a multiple of 64: (column within a 64-wide k-block, row, k-block). One TMA
+// instruction then fetches `box_kb` consecutive k-blocks of `box_rows` rows as consecutive SWIZZLE_128B tiles; the TMA
+// unit spends ~600 cycles per instruction whatever the box size (tests/gpu probes), so big boxes are what feeds the MMA.
+bool make_tmap_kblocks(CUtensorMap* tm, const void* base, long long rows, long long K, long long ld_elems, int box_rows,
+                       int box_kb) {
+  PFN_encodeTiled enc = get_encode_fn();
+  if (enc == nullptr || (K % BK) != 0) return false;
+  cuuint64_t gdim[3] = {static_cast<cuuint64_t>(BK), static_cast<cuuint64_t>(rows), static_cast<cuuint64_t>(K / BK)};
+  cuuint64_t gstr[2] = {static_cast<cuuint64_t>(ld_elems) * 2, static_cast<cuuint64_t>(BK) * 2};
+  cuuint32_t box[3] = {static_cast<cuuint32_t>(BK), static_cast<cuuint32_t>(box_rows), static_cast<cuuint32_t>(box_kb)};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), gdim, gstr, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS;
+}
+
 int pick_block_n(int M, int N, int K, int num_sms, int gran = 32, int max_bn = 256) {
   // Candidates are multiples of the epilogue granularity (32-column chunk, or the TMA slab width) up to the
   // 256-column UMMA limit. Cost model fitted to B200 sweeps (tests/gpu_gemm_shapes.py, SWEEP=1): a tile costs a fixed
@@ -603,11 +980,191 @@ int pick_block_n(int M, int N, int K, int num_sms, int gran = 32, int max_bn = 2
 
 int g_num_sms = 0;
 
+// block_n of the pair kernel: 64-column multiples; cost = waves x operand rows fed per CTA per k-block (+ epilogue)
+int pick_block_n_pair(int M, int N, int num_pairs) {
+  const int cands[] = {256, 192, 128, 64};
+  const long long m_tiles = (M + 2 * BM - 1) / (2 * BM);
+  int best = 64;
+  double best_cost = 1e30;
+  for (int bn : cands) {
+    const long long tiles = m_tiles * ((N + bn - 1) / bn);
+    const double waves = static_cast<double>(tiles) / num_pairs;
+    const double waves_q = waves > 6.0 ? waves : std::ceil(waves);
+    const double cost = waves_q * (128.0 + bn / 2 + 40.0);   // 40: fixed per-tile cost in the same (row) units
+    if (cost < best_cost - 1e-9) { best_cost = cost; best = bn; }
+  }
+  return best;
+}
+
+template <int ACT>
+cudaError_t launch_pair_kernel(long long tiles, size_t smem, cudaStream_t stream, const CUtensorMap& tmA,
+                               const CUtensorMap& tmB, const CUtensorMap& tmRes, const CUtensorMap& tmOut,
+                               const FastParams& p) {
+  // persistent over tiles: exactly the clusters that can be co-resident (a cluster left over would run alone afterwards)
+  static int max_clusters = 0;
+  if (max_clusters == 0) {
+    cudaLaunchConfig_t q = {};
+    q.gridDim = dim3(g_num_sms);
+    q.blockDim = dim3(FAST_THREADS);
+    q.dynamicSmemBytes = SMEM_BUDGET + 1024;
+    cudaLaunchAttribute qa[1];
+    qa[0].id = cudaLaunchAttributeClusterDimension;
+    qa[0].val.clusterDim.x = 2; qa[0].val.clusterDim.y = 1; qa[0].val.clusterDim.z = 1;
+    q.attrs = qa; q.numAttrs = 1;
+    int n = 0;
+    if (cudaOccupancyMaxActiveClusters(&n, gemm_bf16_tcgen05_pair_kernel<ACT>, &q) != cudaSuccess || n < 1) n = g_num_sms / 2;
+    if (n > g_num_sms / 2) n = g_num_sms / 2;
+    max_clusters = n;
+    if (std::getenv("FMMT_DEBUG") != nullptr) fprintf(stderr, "[fmmt] co-resident CTA pairs: %d\n", n);
+  }
+  const int grid = 2 * static_cast<int>(tiles < max_clusters ? tiles : max_clusters);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(FAST_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, gemm_bf16_tcgen05_pair_kernel<ACT>, tmA, tmB, tmRes, tmOut, p);
+}
+
+cudaError_t launch_gemm_pair(const GemmArgs& a, cudaStream_t stream) {
+  static std::once_flag once;
+  static cudaError_t attr_err = cudaSuccess;
+  std::call_once(once, [] {
+    attr_err = cudaFuncSetAttribute(gemm_bf16_tcgen05_pair_kernel<ACT_NONE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    SMEM_BUDGET + 1024);
+    if (attr_err == cudaSuccess)
+      attr_err = cudaFuncSetAttribute(gemm_bf16_tcgen05_pair_kernel<ACT_GELU>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      SMEM_BUDGET + 1024);
+    if (attr_err == cudaSuccess)
+      attr_err = cudaFuncSetAttribute(gemm_bf16_tcgen05_pair_kernel<ACT_TANH>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      SMEM_BUDGET + 1024);
+  });
+  if (attr_err != cudaSuccess) return attr_err;
+  const int num_pairs = g_num_sms / 2;
+  FastParams p{};
+  p.M = a.M; p.N = a.N; p.K = a.K;
+  p.out_bf16 = a.out_bf16 != nullptr;
+  p.slab_cols = p.out_bf16 ? 64 : 32;
+  p.has_res = a.residual != nullptr;
+  p.block_n = a.block_n > 0 ? a.block_n : pick_block_n_pair(a.M, a.N, num_pairs);
+  if (p.block_n % 64 != 0 || p.block_n < 64 || p.block_n > 256) return cudaErrorInvalidValue;
+  static const int env_kbs = std::getenv("FMMT_PAIR_KBS") ? atoi(std::getenv("FMMT_PAIR_KBS")) : 0;
+  static const int env_stages = std::getenv("FMMT_PAIR_STAGES") ? atoi(std::getenv("FMMT_PAIR_STAGES")) : 0;
+  static const int env_groups = std::getenv("FMMT_PAIR_GROUPS") ? atoi(std::getenv("FMMT_PAIR_GROUPS")) : 0;
+  p.kbs = ((a.K % BK) == 0 && a.K >= 2 * BK && env_kbs != 1) ? 2 : 1;   // 3-D tensor maps need whole k-blocks
+  p.stage_bytes = p.kbs * (A_TILE_BYTES + (p.block_n / 2) * BK * 2);
+  p.groups = (a.K >= 512) ? 2 : EPI_GROUPS;
+  if (env_groups == 2 || env_groups == 4) p.groups = env_groups;
+  int ring = (p.has_res ? 2 : 1) * p.groups * SLAB_BYTES;
+  if ((SMEM_BUDGET - ring) / p.stage_bytes < 2 && p.groups > 2) {   // pipeline depth before epilogue groups
+    p.groups = 2;
+    ring = (p.has_res ? 2 : 1) * p.groups * SLAB_BYTES;
+  }
+  if ((SMEM_BUDGET - ring) / p.stage_bytes < 2 && p.kbs > 1) {
+    p.kbs = 1;
+    p.stage_bytes = A_TILE_BYTES + (p.block_n / 2) * BK * 2;
+  }
+  p.num_stages = (SMEM_BUDGET - ring) / p.stage_bytes;
+  if (p.num_stages > MAX_STAGES) p.num_stages = MAX_STAGES;
+  if (env_stages >= 2 && env_stages < p.num_stages) p.num_stages = env_stages;
+  if (p.num_stages < 2) return cudaErrorInvalidValue;
+  p.m_tiles = (a.M + 2 * BM - 1) / (2 * BM);
+  p.n_tiles = (a.N + p.block_n - 1) / p.block_n;
+  p.num_kb = (a.K + BK - 1) / BK;
+  p.bias = a.bias; p.act = a.act;
+  CUtensorMap tmA, tmB, tmRes, tmOut;
+  if (p.kbs > 1 && !(make_tmap_kblocks(&tmA, a.A, a.M, a.K, a.lda, BM, p.kbs) &&
+                     make_tmap_kblocks(&tmB, a.W, a.N, a.K, a.ldw, p.block_n / 2, p.kbs))) {
+    static bool warned = false;
+    if (!warned && std::getenv("FMMT_DEBUG") != nullptr) fprintf(stderr, "[fmmt] 3-D tensor map rejected; 2-D k-blocks\n");
+    warned = true;
+    p.kbs = 1;   // same stage footprint budget: recompute the pipeline shape
+    p.stage_bytes = A_TILE_BYTES + (p.block_n / 2) * BK * 2;
+    p.num_stages = (SMEM_BUDGET - ring) / p.stage_bytes;
+    if (p.num_stages > MAX_STAGES) p.num_stages = MAX_STAGES;
+  }
+  if (p.kbs == 1) {
+    if (!make_tmap(&tmA, a.A, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, a.M, a.K, a.lda, BK, BM)) return cudaErrorInvalidValue;
+    if (!make_tmap(&tmB, a.W, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, a.N, a.K, a.ldw, BK, p.block_n / 2)) return cudaErrorInvalidValue;
+  }
+  if (p.out_bf16) {
+    if (!make_tmap(&tmOut, a.out_bf16, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, a.M, a.N, a.ldo16, 64, BM)) return cudaErrorInvalidValue;
+  } else {
+    if (!make_tmap(&tmOut, a.out_f32, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, a.M, a.N, a.ldo32, 32, BM)) return cudaErrorInvalidValue;
+  }
+  if (p.has_res) {
+    if (!make_tmap(&tmRes, a.residual, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, a.M, a.N, a.ldr, 32, BM)) return cudaErrorInvalidValue;
+  } else {
+    tmRes = tmOut;
+  }
+  const long long tiles = static_cast<long long>(p.m_tiles) * p.n_tiles;
+  const size_t smem = static_cast<size_t>(p.num_stages) * p.stage_bytes + ring + 1024;
+  if (a.act == ACT_NONE) return launch_pair_kernel<ACT_NONE>(tiles, smem, stream, tmA, tmB, tmRes, tmOut, p);
+  if (a.act == ACT_GELU) return launch_pair_kernel<ACT_GELU>(tiles, smem, stream, tmA, tmB, tmRes, tmOut, p);
+  return launch_pair_kernel<ACT_TANH>(tiles, smem, stream, tmA, tmB, tmRes, tmOut, p);
+}
+
 }  // namespace
 
 bool make_tmap_2d(CUtensorMap* tm, const void* base, CUtensorMapDataType dt, int esize, long long rows, long long cols,
                   long long ld_elems, int box_cols, int box_rows) {
   return make_tmap(tm, base, dt, esize, rows, cols, ld_elems, box_cols, box_rows);
+}
+
+double mma_rate_probe(int n, int iters) {
+  long long* d = nullptr;
+  if (cudaMalloc(&d, sizeof(long long)) != cudaSuccess) return -1.0;
+  cudaMemset(d, 0, sizeof(long long));
+  const size_t smem = A_TILE_BYTES + 256 * 128 + 1024;
+  cudaFuncSetAttribute(mma_rate_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  mma_rate_probe_kernel<<<sms, 128, smem>>>(n, iters, d);
+  long long h = 0;
+  cudaError_t e = cudaMemcpy(&h, d, sizeof(h), cudaMemcpyDeviceToHost);
+  cudaFree(d);
+  if (e != cudaSuccess) return -1.0;
+  return static_cast<double>(h) / (4.0 * iters);   // cycles per MMA
+}
+
+int feed_probe(int iters, int nstage, int box_rows, int mode, int grid, double* out2) {
+  if (nstage < 1 || nstage > MAX_STAGES || box_rows < 8 || box_rows > 256 || (box_rows % 8) != 0) return -1;
+  const int rows_total = 1 << 18;   // 256K rows x 64 bf16 = 32 MB: L2-resident after the first pass
+  __nv_bfloat16* buf = nullptr;
+  long long* d = nullptr;
+  if (cudaMalloc(&buf, static_cast<size_t>(rows_total) * 128) != cudaSuccess) return -1;
+  cudaMemset(buf, 0, static_cast<size_t>(rows_total) * 128);
+  cudaMalloc(&d, 2 * sizeof(long long));
+  cudaMemset(d, 0, 2 * sizeof(long long));
+  CUtensorMap tm;
+  int rc = -1;
+  if (make_tmap(&tm, buf, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, rows_total, 64, 64, 64, box_rows)) {
+    const size_t smem = static_cast<size_t>(nstage) * box_rows * 128 + A_TILE_BYTES + 256 * 128 + 1024;
+    if (smem <= static_cast<size_t>(SMEM_BUDGET + 1024)) {
+      cudaFuncSetAttribute(feed_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+      for (int rep = 0; rep < 2; ++rep) {   // first pass warms L2
+        cudaMemset(d, 0, 2 * sizeof(long long));
+        feed_probe_kernel<<<grid, 128, smem>>>(tm, iters, nstage, box_rows, rows_total, mode, d);
+      }
+      long long h[2] = {0, 0};
+      if (cudaMemcpy(h, d, sizeof(h), cudaMemcpyDeviceToHost) == cudaSuccess) {
+        out2[0] = static_cast<double>(iters) * box_rows * 128 / static_cast<double>(h[0] > 0 ? h[0] : 1);   // bytes per cycle per SM
+        out2[1] = h[1] > 0 ? static_cast<double>(h[1]) / (iters * box_rows / 96) : 0.0;                     // cycles per MMA
+        rc = 0;
+      }
+    }
+  }
+  cudaFree(buf);
+  cudaFree(d);
+  return rc;
 }
 
 unsigned int read_mbar_timeout(bool reset) {
@@ -645,18 +1202,27 @@ cudaError_t launch_gemm(const GemmArgs& a, cudaStream_t stream) {
   const bool fast = !a.force_generic && one_out && a.row_map == nullptr && a.rows_in == 0 && a.res_mod == 0 &&
                     (a.residual == nullptr || a.out_f32 != nullptr) && a.N >= 32;
   CUtensorMap tmA, tmB;
+  if (fast && a.N >= 64) {
+    // CTA pairs where the operand feed bounds the tile (K >= 256) and there are enough 256-row tiles; two_cta: 1 forces,
+    // -1 forbids (FMMT_NO_2CTA=1 in the environment forbids globally: A/B runs)
+    static const bool no_pair = std::getenv("FMMT_NO_2CTA") != nullptr;
+    static const bool pair_default = std::getenv("FMMT_2CTA") != nullptr;   // measured no faster than single CTAs
+    const bool want = a.two_cta > 0 || (a.two_cta == 0 && !no_pair && pair_default && a.K >= 256 && a.M >= 1024 && a.N >= 128);
+    if (want) return launch_gemm_pair(a, stream);
+  }
   if (fast) {
     static std::once_flag once2;
     static cudaError_t attr_err2 = cudaSuccess;
     std::call_once(once2, [] {
-      attr_err2 = cudaFuncSetAttribute(gemm_bf16_tcgen05_tma_kernel<ACT_NONE>,
-                                       cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BUDGET + 1024);
-      if (attr_err2 == cudaSuccess)
-        attr_err2 = cudaFuncSetAttribute(gemm_bf16_tcgen05_tma_kernel<ACT_GELU>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BUDGET + 1024);
-      if (attr_err2 == cudaSuccess)
-        attr_err2 = cudaFuncSetAttribute(gemm_bf16_tcgen05_tma_kernel<ACT_TANH>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BUDGET + 1024);
+      const void* fns[6] = {reinterpret_cast<const void*>(gemm_bf16_tcgen05_tma_kernel<ACT_NONE, 1>),
+                            reinterpret_cast<const void*>(gemm_bf16_tcgen05_tma_kernel<ACT_GELU, 1>),
+                            reinterpret_cast<const void*>(gemm_bf16_tcgen05_tma_kernel<ACT_TANH, 1>),
+                            reinterpret_cast<const void*>(gemm_bf16_tcgen05_tma_kernel<ACT_NONE, 2>),
+                            reinterpret_cast<const void*>(gemm_bf16_tcgen05_tma_kernel<ACT_GELU, 2>),
+                            reinterpret_cast<const void*>(gemm_bf16_tcgen05_tma_kernel<ACT_TANH, 2>)};
+      for (const void* f : fns)
+        if (attr_err2 == cudaSuccess)
+          attr_err2 = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BUDGET + 1024);
     });
     if (attr_err2 != cudaSuccess) return attr_err2;
     FastParams p{};
@@ -666,6 +1232,7 @@ cudaError_t launch_gemm(const GemmArgs& a, cudaStream_t stream) {
     p.has_res = a.residual != nullptr;
     p.block_n = a.block_n > 0 ? a.block_n : pick_block_n(a.M, a.N, a.K, g_num_sms, p.slab_cols, 256);
     if (p.block_n % p.slab_cols != 0 || p.block_n < 32 || p.block_n > 256) return cudaErrorInvalidValue;
+    p.kbs = 1;
     p.stage_bytes = A_TILE_BYTES + p.block_n * BK * 2;
     // epilogue-bound shapes (small K) want all 4 groups; compute-bound ones want pipeline depth
     p.groups = (a.K >= 512) ? 2 : EPI_GROUPS;
@@ -675,6 +1242,25 @@ cudaError_t launch_gemm(const GemmArgs& a, cudaStream_t stream) {
       ring = (p.has_res ? 2 : 1) * p.groups * SLAB_BYTES;
     }
     p.num_stages = (SMEM_BUDGET - ring) / p.stage_bytes;
+    // The TMA unit spends ~600 cycles per instruction for boxes up to 32 KB (feed probe): two k-blocks per instruction
+    // (3-D tensor maps, whole k-blocks only) when at least two such stages still fit.
+    static const int env_kbs1 = std::getenv("FMMT_KBS") ? atoi(std::getenv("FMMT_KBS")) : 0;
+    bool use3d = false;
+    if ((a.K % BK) == 0 && a.K >= 4 * BK && env_kbs1 != 1) {
+      int g2 = p.groups, ring2 = ring;
+      if ((SMEM_BUDGET - ring2) / (2 * p.stage_bytes) < 2 && g2 > 2) {   // trade epilogue groups for big TMA boxes (measured)
+        g2 = 2;
+        ring2 = (p.has_res ? 2 : 1) * g2 * SLAB_BYTES;
+      }
+      if ((SMEM_BUDGET - ring2) / (2 * p.stage_bytes) >= 2) {
+        p.groups = g2;
+        ring = ring2;
+        p.kbs = 2;
+        p.stage_bytes *= 2;
+        p.num_stages = (SMEM_BUDGET - ring) / p.stage_bytes;
+        use3d = true;
+      }
+    }
     if (p.num_stages > MAX_STAGES) p.num_stages = MAX_STAGES;
     if (p.num_stages < 2) return cudaErrorInvalidValue;
     p.m_tiles = (a.M + BM - 1) / BM;
@@ -682,8 +1268,13 @@ cudaError_t launch_gemm(const GemmArgs& a, cudaStream_t stream) {
     p.num_kb = (a.K + BK - 1) / BK;
     p.bias = a.bias; p.act = a.act;
     CUtensorMap tmRes, tmOut;
-    if (!make_tmap(&tmA, a.A, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, a.M, a.K, a.lda, BK, BM)) return cudaErrorInvalidValue;
-    if (!make_tmap(&tmB, a.W, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, a.N, a.K, a.ldw, BK, p.block_n)) return cudaErrorInvalidValue;
+    if (use3d) {
+      if (!make_tmap_kblocks(&tmA, a.A, a.M, a.K, a.lda, BM, 2)) return cudaErrorInvalidValue;
+      if (!make_tmap_kblocks(&tmB, a.W, a.N, a.K, a.ldw, p.block_n, 2)) return cudaErrorInvalidValue;
+    } else {
+      if (!make_tmap(&tmA, a.A, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, a.M, a.K, a.lda, BK, BM)) return cudaErrorInvalidValue;
+      if (!make_tmap(&tmB, a.W, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, a.N, a.K, a.ldw, BK, p.block_n)) return cudaErrorInvalidValue;
+    }
     if (p.out_bf16) {
       if (!make_tmap(&tmOut, a.out_bf16, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, a.M, a.N, a.ldo16, 64, BM)) return cudaErrorInvalidValue;
     } else {
@@ -697,12 +1288,19 @@ cudaError_t launch_gemm(const GemmArgs& a, cudaStream_t stream) {
     const long long tiles = static_cast<long long>(p.m_tiles) * p.n_tiles;
     const int grid = static_cast<int>(tiles < g_num_sms ? tiles : g_num_sms);
     const size_t smem = static_cast<size_t>(p.num_stages) * p.stage_bytes + ring + 1024;
-    if (a.act == ACT_NONE)
-      gemm_bf16_tcgen05_tma_kernel<ACT_NONE><<<grid, FAST_THREADS, smem, stream>>>(tmA, tmB, tmRes, tmOut, p);
+    if (p.kbs == 2) {
+      if (a.act == ACT_NONE)
+        gemm_bf16_tcgen05_tma_kernel<ACT_NONE, 2><<<grid, FAST_THREADS, smem, stream>>>(tmA, tmB, tmRes, tmOut, p);
+      else if (a.act == ACT_GELU)
+        gemm_bf16_tcgen05_tma_kernel<ACT_GELU, 2><<<grid, FAST_THREADS, smem, stream>>>(tmA, tmB, tmRes, tmOut, p);
+      else
+        gemm_bf16_tcgen05_tma_kernel<ACT_TANH, 2><<<grid, FAST_THREADS, smem, stream>>>(tmA, tmB, tmRes, tmOut, p);
+    } else if (a.act == ACT_NONE)
+      gemm_bf16_tcgen05_tma_kernel<ACT_NONE, 1><<<grid, FAST_THREADS, smem, stream>>>(tmA, tmB, tmRes, tmOut, p);
     else if (a.act == ACT_GELU)
-      gemm_bf16_tcgen05_tma_kernel<ACT_GELU><<<grid, FAST_THREADS, smem, stream>>>(tmA, tmB, tmRes, tmOut, p);
+      gemm_bf16_tcgen05_tma_kernel<ACT_GELU, 1><<<grid, FAST_THREADS, smem, stream>>>(tmA, tmB, tmRes, tmOut, p);
     else  // runtime-switched activation (ReLU / tanh)
-      gemm_bf16_tcgen05_tma_kernel<ACT_TANH><<<grid, FAST_THREADS, smem, stream>>>(tmA, tmB, tmRes, tmOut, p);
+      gemm_bf16_tcgen05_tma_kernel<ACT_TANH, 1><<<grid, FAST_THREADS, smem, stream>>>(tmA, tmB, tmRes, tmOut, p);
     return cudaGetLastError();
   }
 

@@ -34,6 +34,7 @@ struct GemmArgs {
   int rows_in = 0, rows_out = 0, row_off = 0;  // if rows_in>0: dest = (r/rows_in)*rows_out + row_off + r%rows_in
   int block_n = 0;                  // 0 = choose automatically
   int force_generic = 0;            // 1 = register-path epilogue even where the TMA-epilogue fast path applies
+  int two_cta = 0;                  // CTA-pair kernel (cta_group::2, 256-row tiles): 0 = heuristic, 1 = force, -1 = never
 };
 
 // Returns cudaSuccess or the launch / tensor-map error. Asynchronous on `stream`.
@@ -47,6 +48,14 @@ bool make_tmap_2d(CUtensorMap* tm, const void* base, CUtensorMapDataType dt, int
 // Non-zero if a pipeline wait inside a GEMM kernel timed out since the last reset (a protocol bug): bit 31 set,
 // bits 24-30 = which barrier, 12-23 = CTA, 0-11 = thread. Synchronises the device.
 unsigned int read_mbar_timeout(bool reset);
+
+// Tensor-pipe probe (bench only): cycles per tcgen05.mma (M = 128, N = n, K = 16, bf16) with operands resident in
+// shared memory and no other traffic; all SMs run it at once. Synchronous.
+double mma_rate_probe(int n, int iters);
+
+// Feed probe (bench only): TMA bytes per cycle per SM from an L2-resident matrix (out2[0]) with `nstage` boxes of
+// 64 x box_rows bf16 in flight on `grid` CTAs; mode 1 runs N = 256 MMAs beside it and reports cycles per MMA (out2[1]).
+int feed_probe(int iters, int nstage, int box_rows, int mode, int grid, double* out2);
 
 // Algorithmic work of one launch (2*M*N*K) for roofline accounting.
 inline double gemm_flops(const GemmArgs& a) { return 2.0 * a.M * (double)a.N * a.K; }

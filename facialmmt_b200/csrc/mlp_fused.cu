@@ -229,7 +229,7 @@ swin_mlp96_fused_kernel(const __grid_constant__ CUtensorMap tmX, const Mlp96Para
         v += __shfl_xor_sync(0xffffffffu, v, 4);
         rstd[q] = rsqrtf(v * (1.0f / MLP96_C) + p.eps);
       }
-      mbar_wait(&a_empty, (i & 1u) ^ 1u, 22);    // fc1 of the previous tile has consumed the A tile
+      mbar_wait_relaxed(&a_empty, (i & 1u) ^ 1u, 22);    // fc1 of the previous tile has consumed the A tile
 #pragma unroll
       for (int j = 0; j < 3; ++j) {
         const int col = 4 * l8 + 32 * j;         // 0..95
@@ -259,7 +259,7 @@ swin_mlp96_fused_kernel(const __grid_constant__ CUtensorMap tmX, const Mlp96Para
     uint8_t* my_out = smem + OFF_IO + row * 128;
     auto drain_tile = [&](int i) {
       const int m0 = (static_cast<int>(blockIdx.x) + i * static_cast<int>(gridDim.x)) * TILE_M;
-      mbar_wait(&out_full, i & 1u, 23);
+      mbar_wait_relaxed(&out_full, i & 1u, 23, 500);
       tc_fence_after();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + TM_OUT;
 #pragma unroll 1

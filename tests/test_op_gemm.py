@@ -125,3 +125,38 @@ def test_gemm_streaming_many_tiles(lib, N, K, res, out16):
     residual/out rings and the slab->group assignment cycle many times (regression for a ring-parity aliasing bug)."""
     for _ in range(4):
         _run(lib, 100352, N, K, bias=True, residual=res, out16=out16, out32=not out16, act=1 if out16 else 0)
+
+
+@pytest.mark.parametrize("M,N,K,bn", [
+    (256, 256, 64, 256), (256, 128, 256, 128), (300, 192, 256, 192), (128, 256, 384, 256), (1000, 384, 384, 0),
+    (2048, 1536, 384, 0), (196 * 16, 1152, 384, 0), (196 * 16, 384, 1536, 0), (49 * 40, 3072, 768, 0),
+    (1024, 4096, 1024, 0), (1030, 96, 512, 0), (31360, 1536, 384, 0), (5000, 200, 320, 0),
+])
+def test_gemm_cta_pair(lib, M, N, K, bn):
+    """CTA-pair kernel (tcgen05 cta_group::2, 256-row tiles, block_n code 1000 + bn): same contract as the single-CTA
+    kernels, incl. ragged M (second CTA of the last pair partly or wholly out of range), ragged N and K % 64 != 0."""
+    code = 1000 + bn
+    _run(lib, M, N, K, block_n=code)
+    _run(lib, M, N, K, block_n=code, bias=True, residual=True)
+    if N % 8 == 0:
+        _run(lib, M, N, K, block_n=code, bias=True, act=1, out16=True, out32=False)
+    assert lib.fmmt_debug_timeout(1) == 0, "pipeline wait timed out inside the CTA-pair GEMM"
+
+
+def test_gemm_cta_pair_matches_single(lib):
+    """same operands through both kernels: fp32 accumulation order over K is identical (k-blocks in order), so the
+    results must agree bit for bit"""
+    from facialmmt_b200._lib import check, cur_stream, ptr
+    g = torch.Generator(device="cpu").manual_seed(5)
+    M, N, K = 3000, 768, 1536
+    A = torch.randn(M, K, generator=g).to(torch.bfloat16).cuda()
+    W = (torch.randn(N, K, generator=g) / K ** 0.5).to(torch.bfloat16).cuda()
+    outs = []
+    for code in (999, 1000):
+        o = torch.empty(M, N, device="cuda")
+        check(lib.fmmt_op_gemm(ptr(A), K, ptr(W), K, M, N, K, None, 0, None, 0, ptr(o), N, None, 0, None, 0, code,
+                               cur_stream()))
+        outs.append(o)
+    torch.cuda.synchronize()
+    assert lib.fmmt_debug_timeout(1) == 0
+    assert torch.equal(outs[0], outs[1])
