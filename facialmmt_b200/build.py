@@ -17,7 +17,7 @@ CSRC = PKG_DIR / "csrc"
 BUILD_DIR = CSRC / "build"
 LIB_PATH = PKG_DIR / "libfacialmmt_b200.so"
 
-SOURCES = ["gemm.cu", "mlp_fused.cu", "kernels.cu", "attention.cu", "engine.cu", "capi.cu"]
+SOURCES = ["gemm.cu", "mlp_fused.cu", "mlp_stream.cu", "kernels.cu", "attention.cu", "engine.cu", "capi.cu"]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

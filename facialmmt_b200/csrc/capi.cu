@@ -120,7 +120,8 @@ FMMT_API int64_t fmmt_profile_read(fmmt_handle* h, char* buf, int64_t buf_len) {
 FMMT_API uint32_t fmmt_debug_timeout(int reset) {
   const uint32_t a = read_mbar_timeout(reset != 0);
   const uint32_t b = read_mlp_timeout(reset != 0);
-  return a != 0 ? a : b;
+  const uint32_t c = read_mlp_stream_timeout(reset != 0);
+  return a != 0 ? a : (b != 0 ? b : c);
 }
 
 FMMT_API double fmmt_debug_mma_cycles(int n, int iters) { return mma_rate_probe(n, iters); }
@@ -188,6 +189,19 @@ FMMT_API int fmmt_op_swin_mlp(float* x, int M, const float* gamma, const float* 
   a.img = static_cast<const __nv_bfloat16*>(img_dev); a.b1 = b1; a.b2 = b2;
   count_launch();
   return check_cuda(launch_mlp96(a, S(stream)), "fmmt_op_swin_mlp");
+}
+
+FMMT_API int fmmt_op_swin_mlp_stream(float* x, int M, int C, const float* gamma, const float* beta, float eps,
+                                     const void* w1_bf16, int ldw1, const float* b1, const void* w2_bf16, int ldw2,
+                                     const float* b2, void* stream) {
+  if (!x || !gamma || !beta || !w1_bf16 || !w2_bf16 || !b1 || !b2)
+    return set_error(FMMT_ERR_INVALID, "fmmt_op_swin_mlp_stream: null pointer");
+  MlpStreamArgs a;
+  a.x = x; a.M = M; a.C = C; a.gamma = gamma; a.beta = beta; a.eps = eps;
+  a.w1 = static_cast<const __nv_bfloat16*>(w1_bf16); a.ldw1 = ldw1; a.b1 = b1;
+  a.w2 = static_cast<const __nv_bfloat16*>(w2_bf16); a.ldw2 = ldw2; a.b2 = b2;
+  count_launch();
+  return check_cuda(launch_mlp_stream(a, S(stream)), "fmmt_op_swin_mlp_stream");
 }
 
 FMMT_API int fmmt_op_window_attention(const void* qkv_bf16, void* out_bf16, const float* bias, const int8_t* rid,

@@ -585,6 +585,22 @@ void Engine::mlp96(float* x, int M, const SwinBlockW& bw) {
   if (prof_) prof_end(e1);
 }
 
+void Engine::mlp_stream(float* x, int M, int C, const SwinBlockW& bw) {
+  if (arena_.dry() || first_err_ != cudaSuccess) return;
+  flops_ += mlp_stream_flops(M, C);
+  count_launch();
+  cudaEvent_t e1 = nullptr;
+  if (prof_) e1 = prof_begin("mlp_fused C=" + std::to_string(C) + " M=" + std::to_string(M), mlp_stream_flops(M, C),
+                             8.0 * M * C + 2.0 * 2.0 * C * 4.0 * C);
+  MlpStreamArgs a;
+  a.x = x; a.M = M; a.C = C;
+  a.gamma = bw.ln2.g; a.beta = bw.ln2.b; a.eps = 1e-5f;
+  a.w1 = bw.fc1.w; a.ldw1 = bw.fc1.ld; a.b1 = bw.fc1.b;
+  a.w2 = bw.fc2.w; a.ldw2 = bw.fc2.ld; a.b2 = bw.fc2.b;
+  ck(launch_mlp_stream(a, st_), "mlp_stream");
+  if (prof_) prof_end(e1);
+}
+
 void Engine::capture(const std::string& name, const float* src, size_t count, size_t dst_off) {
   if (arena_.dry() || first_err_ != cudaSuccess || caps_.empty()) return;
   auto it = caps_.find(name);
@@ -679,6 +695,11 @@ void Engine::swin_block(const SwinStageW& sw, const SwinBlockW& bw, float*& x, f
   gemm_lin(a, C, M, bw.proj, g2);
   if (bw.mlp_img != nullptr) {                                      // stage 1: norm2 + fc1 + GELU + fc2 + residual fused
     mlp96(x, M, bw);
+    return;
+  }
+  static const bool no_stream = std::getenv("FMMT_NO_MLP_STREAM") != nullptr;
+  if (!no_stream && mlp_stream_supported(C, bw.fc1.N) && bw.fc1.b && bw.fc2.b) {   // stages 2-3: same, weights streamed
+    mlp_stream(x, M, C, bw);
     return;
   }
   LnArgs l2;

@@ -12,6 +12,7 @@
 #include "facialmmt_b200.h"
 #include "gemm.cuh"
 #include "mlp_fused.cuh"
+#include "mlp_stream.cuh"
 #include "ops.cuh"
 
 namespace fmmt {
@@ -179,6 +180,7 @@ class Engine {
   void gemm_lin(const bf16* A, int lda, int M, const Lin& l, GemmArgs ep);
   void ln(LnArgs a);
   void mlp96(float* x, int M, const SwinBlockW& bw);
+  void mlp_stream(float* x, int M, int C, const SwinBlockW& bw);
   void ck(cudaError_t e, const char* what);
   void capture(const std::string& name, const float* src, size_t count, size_t dst_off = 0);
 

@@ -522,6 +522,9 @@ gemm_bf16_tcgen05_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __gr
               v[4 * j + 2] = __float_as_uint(__uint_as_float(v[4 * j + 2]) + r.z);
               v[4 * j + 3] = __float_as_uint(__uint_as_float(v[4 * j + 3]) + r.w);
             }
+            // generic-proxy reads of the slab must be ordered before the async-proxy (TMA) refill that this arrival
+            // allows: without the proxy fence a read still queued in the memory pipe can see the NEXT slab's bytes
+            fence_proxy_async_smem();
             mbar_arrive(&res_empty_bar[slot]);               // this thread is done reading the residual slab
           }
           if (elected) tma_store_wait_read<0>();
@@ -769,6 +772,7 @@ gemm_bf16_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __g
               v[4 * j + 2] = __float_as_uint(__uint_as_float(v[4 * j + 2]) + r.z);
               v[4 * j + 3] = __float_as_uint(__uint_as_float(v[4 * j + 3]) + r.w);
             }
+            fence_proxy_async_smem();                        // as in the single-CTA kernel: reads before the TMA refill
             mbar_arrive(&res_empty_bar[slot]);
           }
           if (elected) tma_store_wait_read<0>();
@@ -1116,6 +1120,10 @@ cudaError_t launch_gemm_pair(const GemmArgs& a, cudaStream_t stream) {
 bool make_tmap_2d(CUtensorMap* tm, const void* base, CUtensorMapDataType dt, int esize, long long rows, long long cols,
                   long long ld_elems, int box_cols, int box_rows) {
   return make_tmap(tm, base, dt, esize, rows, cols, ld_elems, box_cols, box_rows);
+}
+bool make_tmap_kblocks_2d(CUtensorMap* tm, const void* base, long long rows, long long K, long long ld_elems, int box_rows,
+                          int box_kb) {
+  return make_tmap_kblocks(tm, base, rows, K, ld_elems, box_rows, box_kb);
 }
 
 double mma_rate_probe(int n, int iters) {

@@ -45,6 +45,11 @@ cudaError_t launch_gemm(const GemmArgs& a, cudaStream_t stream);
 bool make_tmap_2d(CUtensorMap* tm, const void* base, CUtensorMapDataType dt, int esize, long long rows, long long cols,
                   long long ld_elems, int box_cols, int box_rows);
 
+// 3-D view of a K-major bf16 matrix with K % 64 == 0: (column within a 64-wide k-block, row, k-block index); one box =
+// `box_kb` consecutive k-blocks of `box_rows` rows, landing as consecutive SWIZZLE_128B [box_rows x 128 B] tiles.
+bool make_tmap_kblocks_2d(CUtensorMap* tm, const void* base, long long rows, long long K, long long ld_elems, int box_rows,
+                          int box_kb);
+
 // Non-zero if a pipeline wait inside a GEMM kernel timed out since the last reset (a protocol bug): bit 31 set,
 // bits 24-30 = which barrier, 12-23 = CTA, 0-11 = thread. Synchronises the device.
 unsigned int read_mbar_timeout(bool reset);

@@ -160,3 +160,25 @@ def test_gemm_cta_pair_matches_single(lib):
     torch.cuda.synchronize()
     assert lib.fmmt_debug_timeout(1) == 0
     assert torch.equal(outs[0], outs[1])
+
+
+def test_gemm_inplace_residual_stress(lib):
+    """out_f32 == residual (how the engine applies every shortcut): the epilogue reads the TMA-loaded residual slab through
+    the generic proxy and then lets the async proxy refill it; without a proxy fence before the release a late read saw the
+    next slab's bytes in ~1 of 3 launches at these shapes (rows of one 16-byte chunk off by a whole residual)."""
+    from facialmmt_b200._lib import check, cur_stream, ptr
+    g = torch.Generator(device="cpu").manual_seed(3)
+    N, K = 384, 1536
+    W = (torch.randn(N, K, generator=g) / K ** 0.5).to(torch.bfloat16).cuda()
+    b = torch.randn(N, generator=g).cuda()
+    for M in (148 * 128, 31360):
+        for rep in range(12):
+            A = torch.randn(M, K, generator=g).to(torch.bfloat16).cuda()
+            x = torch.randn(M, N, generator=g).cuda()
+            y = x.clone()
+            check(lib.fmmt_op_gemm(ptr(A), K, ptr(W), K, M, N, K, ptr(b), 0, ptr(y), N, ptr(y), N, None, 0, None, 0, 0,
+                                   cur_stream()))
+            torch.cuda.synchronize()
+            ref = x + A.float() @ W.float().t() + b
+            err = (y - ref).abs().max().item()
+            assert err < 2e-2, f"M={M} rep={rep}: max err {err}"

@@ -165,3 +165,41 @@ def test_swin_mlp_fused_repeatable(lib):
     y1, _ = _mlp96_case(lib, 148 * 128 * 2 + 5, seed=7)
     y2, _ = _mlp96_case(lib, 148 * 128 * 2 + 5, seed=7)
     assert torch.equal(y1, y2)
+
+
+def _mlp_stream_case(lib, M, C, seed):
+    """fused LN + fc1 + GELU + fc2 + residual with streamed weights (fmmt_op_swin_mlp_stream) against an fp32 torch
+    restatement that rounds the same operands to bf16 (LN output, weights, hidden)."""
+    from facialmmt_b200._lib import check, cur_stream, ptr
+    g = _gen(seed)
+    H = 4 * C
+    x = (torch.randn(M, C, generator=g) * 2 + 0.5).cuda()
+    gam, bet = (1 + 0.2 * torch.randn(C, generator=g)).cuda(), (0.2 * torch.randn(C, generator=g)).cuda()
+    w1 = (torch.randn(H, C, generator=g) / math.sqrt(C)).cuda().to(torch.bfloat16).contiguous()
+    w2 = (torch.randn(C, H, generator=g) / math.sqrt(H)).cuda().to(torch.bfloat16).contiguous()
+    b1, b2 = (0.3 * torch.randn(H, generator=g)).cuda(), (0.3 * torch.randn(C, generator=g)).cuda()
+    bf = lambda t: t.to(torch.bfloat16).float()
+    h = bf(torch.nn.functional.layer_norm(x, (C,), gam, bet, 1e-5))
+    hid = bf(torch.nn.functional.gelu(h @ w1.float().t() + b1))
+    ref = x + (hid @ w2.float().t() + b2)
+    y = x.clone()
+    check(lib.fmmt_op_swin_mlp_stream(ptr(y), M, C, ptr(gam), ptr(bet), 1e-5, ptr(w1), C, ptr(b1), ptr(w2), H, ptr(b2),
+                                      cur_stream()))
+    torch.cuda.synchronize()
+    assert lib.fmmt_debug_timeout(1) == 0, "pipeline wait timed out inside the streamed fused MLP kernel"
+    return y, ref
+
+
+@pytest.mark.parametrize("C", [192, 384])
+@pytest.mark.parametrize("M", [128, 100, 1, 129, 148 * 128, 148 * 128 * 2 + 77, 31360])
+def test_swin_mlp_stream(lib, M, C):
+    y, ref = _mlp_stream_case(lib, M, C, seed=M + C)
+    err = (y - ref).abs().max().item()
+    assert torch.isfinite(y).all()
+    assert err < 2e-2 * max(1.0, ref.abs().max().item() / 8), f"M={M} C={C}: max abs err {err}"
+
+
+def test_swin_mlp_stream_repeatable(lib):
+    y1, _ = _mlp_stream_case(lib, 148 * 128 * 2 + 5, 384, seed=11)
+    y2, _ = _mlp_stream_case(lib, 148 * 128 * 2 + 5, 384, seed=11)
+    assert torch.equal(y1, y2)
