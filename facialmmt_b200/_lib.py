@@ -71,7 +71,7 @@ SIGNATURES = {
     "fmmt_op_swin_mlp_pack": (c_int, [c_void_p, c_void_p, c_void_p]),
     "fmmt_op_swin_mlp": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_float, c_void_p, c_void_p, c_void_p, c_void_p]),
     "fmmt_op_swin_mlp_stream": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_float, c_void_p, c_int, c_void_p,
-                                        c_void_p, c_int, c_void_p, c_void_p]),
+                                        c_void_p, c_int, c_void_p, c_int, c_void_p]),
     "fmmt_op_mha": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_void_p, c_float,
                             c_int, c_int, c_int, c_int, c_float, c_void_p]),
 }

@@ -193,13 +193,16 @@ FMMT_API int fmmt_op_swin_mlp(float* x, int M, const float* gamma, const float* 
 
 FMMT_API int fmmt_op_swin_mlp_stream(float* x, int M, int C, const float* gamma, const float* beta, float eps,
                                      const void* w1_bf16, int ldw1, const float* b1, const void* w2_bf16, int ldw2,
-                                     const float* b2, void* stream) {
+                                     const float* b2, int copies, void* stream) {
   if (!x || !gamma || !beta || !w1_bf16 || !w2_bf16 || !b1 || !b2)
     return set_error(FMMT_ERR_INVALID, "fmmt_op_swin_mlp_stream: null pointer");
   MlpStreamArgs a;
   a.x = x; a.M = M; a.C = C; a.gamma = gamma; a.beta = beta; a.eps = eps;
   a.w1 = static_cast<const __nv_bfloat16*>(w1_bf16); a.ldw1 = ldw1; a.b1 = b1;
   a.w2 = static_cast<const __nv_bfloat16*>(w2_bf16); a.ldw2 = ldw2; a.b2 = b2;
+  a.copies = copies < 0 ? 1 : copies;
+  // debug hook: copies < 0 -> `stream` argument carries a device trace buffer instead (default stream is used)
+  if (copies < 0) { a.trace = static_cast<long long*>(stream); count_launch(); return check_cuda(launch_mlp_stream(a, nullptr), "fmmt_op_swin_mlp_stream"); }
   count_launch();
   return check_cuda(launch_mlp_stream(a, S(stream)), "fmmt_op_swin_mlp_stream");
 }

@@ -80,6 +80,8 @@ struct StreamParams {
   float eps;
   const float* b1;
   const float* b2;
+  int copies;
+  long long* trace;   // optional [CHUNKS][8] clock64 stamps of CTA 0, tile 0 (debug / DESIGN.md timeline)
 };
 
 template <int C>
@@ -133,6 +135,7 @@ swin_mlp_stream_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_co
   const uint32_t tmem_base = tmem_base_slot;
   const int n_local = (p.num_tiles - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) /
                       static_cast<int>(gridDim.x);
+  const int copy = static_cast<int>(blockIdx.x) % p.copies;
 
   if (warp == PROD1_WARP) {
     // ------------------------------------------------------------------ fc1 weight stream (one thread)
@@ -143,8 +146,9 @@ swin_mlp_stream_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_co
           for (int pc = 0; pc < K::PIECES; ++pc, ++u) {
             const uint32_t sl = u & 1u;
             mbar_wait(&w1_empty[sl], ((u >> 1) & 1u) ^ 1u, 40);      // the MMAs on this slot's previous piece are done
+            if (p.trace != nullptr && blockIdx.x == 0 && i == 0 && pc == 0) p.trace[j * 8 + 5] = clock64();   // piece 0 requested
             mbar_arrive_expect_tx(&w1_full[sl], K::W1_PIECE);
-            tma_load_3d(smem + K::OFF_W1 + sl * K::W1_PIECE, &tmW1, &w1_full[sl], 0, 64 * j, 3 * pc);
+            tma_load_3d(smem + K::OFF_W1 + sl * K::W1_PIECE, &tmW1, &w1_full[sl], 0, copy * K::H + 64 * j, 3 * pc);
           }
     }
   } else if (warp == PROD2_WARP) {
@@ -156,8 +160,9 @@ swin_mlp_stream_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_co
           const uint32_t sl = n % K::R2, use = n / K::R2;
           mbar_wait(&w2_empty[sl], (use & 1u) ^ 1u, 41);            // fc2 of this slot's previous chunk is done
           if (i > 0 && j < K::R2) mbar_wait(&drain_done, (i - 1) & 1u, 42);   // ... and the drain staged here is out
+          if (p.trace != nullptr && blockIdx.x == 0 && i == 0) p.trace[j * 8 + 6] = clock64();   // fc2 weights requested
           mbar_arrive_expect_tx(&w2_full[sl], K::W2_BYTES);
-          tma_load_3d(smem + K::OFF_W2 + sl * K::W2_BYTES, &tmW2, &w2_full[sl], 64 * j, 0, 0);
+          tma_load_3d(smem + K::OFF_W2 + sl * K::W2_BYTES, &tmW2, &w2_full[sl], 64 * j, 0, copy * K::NH);
         }
     }
   } else if (warp == MMA_WARP) {
@@ -170,10 +175,13 @@ swin_mlp_stream_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_co
         const uint32_t b = nn & 1u, use = nn >> 1;
         mbar_wait(&d1_empty[b], (use & 1u) ^ 1u, 44);              // the GELU group has drained this buffer's last use
         const uint32_t d = tmem_base + K::TM_D1 + 64u * b;
+        const bool tr = p.trace != nullptr && blockIdx.x == 0 && nn < static_cast<uint32_t>(K::CHUNKS);
+        if (tr) p.trace[nn * 8 + 0] = clock64();                   // d1 buffer free
 #pragma unroll
         for (int pc = 0; pc < K::PIECES; ++pc) {
           const uint32_t u = nn * K::PIECES + pc, sl = u & 1u;
           mbar_wait(&w1_full[sl], (u >> 1) & 1u, 43);
+          if (tr) p.trace[nn * 8 + 1 + pc] = clock64();            // fc1 weight piece landed
           tc_fence_after();
 #pragma unroll
           for (int kk = 0; kk < 3; ++kk) {
@@ -195,8 +203,11 @@ swin_mlp_stream_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_co
           else umma_commit(&a_empty);            // every fc1 of this tile has been issued: A may be rewritten after them
           const uint32_t b = n & 1u, use = n >> 1;
           const uint32_t sl2 = n % K::R2;
+          const bool tr = p.trace != nullptr && blockIdx.x == 0 && i == 0;
           mbar_wait(&w2_full[sl2], (n / K::R2) & 1u, 46);
+          if (tr) p.trace[j * 8 + 3] = clock64();                  // fc2 weights landed
           mbar_wait(&hid_full[b], use & 1u, 47);
+          if (tr) p.trace[j * 8 + 4] = clock64();                  // hidden chunk written
           if (j == 0 && i > 0) mbar_wait(&out_empty, (i - 1) & 1u, 48);   // previous tile's accumulator has been drained
           tc_fence_after();
           const uint64_t a = make_smem_desc_sw128(smem_base + K::OFF_HID + b * 16384);
@@ -337,6 +348,7 @@ swin_mlp_stream_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_co
               make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
         fence_proxy_async_smem();
         mbar_arrive(&hid_full[group]);
+        if (p.trace != nullptr && blockIdx.x == 0 && i == 0 && (threadIdx.x & 255) == 0) p.trace[j * 8 + 7] = clock64();
       }
       if (drains) {
         // fc2 accumulator -> + bias -> 32-column slabs staged in the W2 slot -> TMA reduce-add into x
@@ -389,7 +401,7 @@ swin_mlp_stream_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_co
 }
 
 // 3-D view of fc2.weight [C rows, H cols] (row-major): (column, row within a 192-row half, half)
-bool make_tmap_w2(CUtensorMap* tm, const void* base, int C, int H, int ld) {
+bool make_tmap_w2(CUtensorMap* tm, const void* base, int C, int H, int ld, int copies) {
   typedef CUresult (*PFN)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                           const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                           CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -398,7 +410,7 @@ bool make_tmap_w2(CUtensorMap* tm, const void* base, int C, int H, int ld) {
   if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) != cudaSuccess ||
       qres != cudaDriverEntryPointSuccess)
     return false;
-  cuuint64_t gdim[3] = {static_cast<cuuint64_t>(H), 192, static_cast<cuuint64_t>(C / 192)};
+  cuuint64_t gdim[3] = {static_cast<cuuint64_t>(H), 192, static_cast<cuuint64_t>(C / 192) * copies};
   cuuint64_t gstr[2] = {static_cast<cuuint64_t>(ld) * 2, static_cast<cuuint64_t>(ld) * 2 * 192};
   cuuint32_t box[3] = {64, 192, static_cast<cuuint32_t>(C / 192)};
   cuuint32_t estr[3] = {1, 1, 1};
@@ -421,10 +433,10 @@ cudaError_t launch_c(const MlpStreamArgs& a, cudaStream_t stream) {
   });
   if (attr_err != cudaSuccess) return attr_err;
   CUtensorMap tmW1, tmW2, tmX;
-  if (!make_tmap_kblocks_2d(&tmW1, a.w1, K::H, C, a.ldw1, 64, 3)) return cudaErrorInvalidValue;
-  if (!make_tmap_w2(&tmW2, a.w2, C, K::H, a.ldw2)) return cudaErrorInvalidValue;
+  if (!make_tmap_kblocks_2d(&tmW1, a.w1, static_cast<long long>(K::H) * a.copies, C, a.ldw1, 64, 3)) return cudaErrorInvalidValue;
+  if (!make_tmap_w2(&tmW2, a.w2, C, K::H, a.ldw2, a.copies)) return cudaErrorInvalidValue;
   if (!make_tmap_2d(&tmX, a.x, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, a.M, C, C, 32, TILE_M)) return cudaErrorInvalidValue;
-  StreamParams p{a.x, a.M, (a.M + TILE_M - 1) / TILE_M, a.gamma, a.beta, a.eps, a.b1, a.b2};
+  StreamParams p{a.x, a.M, (a.M + TILE_M - 1) / TILE_M, a.gamma, a.beta, a.eps, a.b1, a.b2, a.copies, a.trace};
   const int grid = p.num_tiles < num_sms ? p.num_tiles : num_sms;
   swin_mlp_stream_kernel<C><<<grid, THREADS, K::SMEM + 1024, stream>>>(tmW1, tmW2, tmX, p);
   return cudaGetLastError();
@@ -443,6 +455,7 @@ unsigned int read_mlp_stream_timeout(bool reset) {
 }
 
 cudaError_t launch_mlp_stream(const MlpStreamArgs& a, cudaStream_t stream) {
+  if (a.copies < 1 || a.copies > 64) return cudaErrorInvalidValue;
   if (a.M <= 0 || !a.x || !a.gamma || !a.beta || !a.w1 || !a.w2 || !a.b1 || !a.b2) return cudaErrorInvalidValue;
   if ((reinterpret_cast<uintptr_t>(a.x) & 15) || (reinterpret_cast<uintptr_t>(a.w1) & 15) ||
       (reinterpret_cast<uintptr_t>(a.w2) & 15) || (reinterpret_cast<uintptr_t>(a.gamma) & 15) ||

@@ -19,6 +19,10 @@ struct MlpStreamArgs {
   const __nv_bfloat16* w2 = nullptr;  // fc2.weight bf16 [C, ldw2]
   int ldw2 = 0;
   const float* b2 = nullptr;     // [C]
+  long long* trace = nullptr;    // optional device buffer [4C/64][8]: clock64 stamps of CTA 0's first tile (debug)
+  int copies = 1;                // w1 / w2 hold `copies` identical matrices stacked along the rows; CTA b streams copy
+                                 // b % copies: every CTA walks the weights in the same order at the same time, and
+                                 // spreading them over several copies spreads those reads over the L2 slices
 };
 inline bool mlp_stream_supported(int C, int H) { return (C == 192 || C == 384) && H == 4 * C; }
 cudaError_t launch_mlp_stream(const MlpStreamArgs& a, cudaStream_t stream);

@@ -166,10 +166,12 @@ FMMT_API int fmmt_op_swin_mlp(float* x, int M, const float* gamma, const float* 
                               const float* b1, const float* b2, void* stream);
 
 /* Same half-block for C = 192 / 384 (hidden 4C): the weights are streamed from L2 per 128-row tile instead of being
- * resident. w1 = fc1.weight as bf16 [4C, ldw1], w2 = fc2.weight as bf16 [C, ldw2] (nn.Linear layout, device pointers). */
+ * resident. w1 = fc1.weight as bf16 [copies * 4C, ldw1], w2 = fc2.weight as bf16 [copies * C, ldw2] (nn.Linear layout,
+ * device pointers; `copies` >= 1 identical matrices stacked along the rows, CTA b reads copy b % copies so that the
+ * lock-step weight walk of all CTAs spreads over the L2 slices). */
 FMMT_API int fmmt_op_swin_mlp_stream(float* x, int M, int C, const float* gamma, const float* beta, float eps,
                                      const void* w1_bf16, int ldw1, const float* b1, const void* w2_bf16, int ldw2,
-                                     const float* b2, void* stream);
+                                     const float* b2, int copies, void* stream);
 
 /* Multi-head attention core, head_dim 64: softmax(scale * q k^T + (1 - key_mask) * mask_neg) v.
  * q rows (b*Lq+i), k/v rows (b*Lk+j), head h at columns [64h, 64h+64). key_mask fp32 (B,Lk) of 0/1 or NULL. */

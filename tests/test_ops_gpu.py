@@ -184,7 +184,7 @@ def _mlp_stream_case(lib, M, C, seed):
     ref = x + (hid @ w2.float().t() + b2)
     y = x.clone()
     check(lib.fmmt_op_swin_mlp_stream(ptr(y), M, C, ptr(gam), ptr(bet), 1e-5, ptr(w1), C, ptr(b1), ptr(w2), H, ptr(b2),
-                                      cur_stream()))
+                                      1, cur_stream()))
     torch.cuda.synchronize()
     assert lib.fmmt_debug_timeout(1) == 0, "pipeline wait timed out inside the streamed fused MLP kernel"
     return y, ref
