@@ -60,6 +60,7 @@ SIGNATURES = {
     "fmmt_debug_timeout": (ctypes.c_uint32, [c_int]),
     "fmmt_debug_mma_cycles": (c_double, [c_int, c_int]),
     "fmmt_debug_feed": (c_int, [c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "fmmt_debug_feed2": (c_double, [c_int, c_int, c_int, c_int, c_int, c_int]),
     "fmmt_flops": (c_double, [c_void_p, c_int]),
     "fmmt_device_bytes": (c_int64, [c_void_p]),
     "fmmt_op_gemm": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int, c_void_p, c_int,

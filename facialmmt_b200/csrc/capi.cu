@@ -124,10 +124,14 @@ FMMT_API uint32_t fmmt_debug_timeout(int reset) {
   return a != 0 ? a : (b != 0 ? b : c);
 }
 
-FMMT_API double fmmt_debug_mma_cycles(int n, int iters) { return mma_rate_probe(n, iters); }
+FMMT_API double fmmt_debug_mma_cycles(int n, int iters) { return mma_rate_probe(n & 0xFFFF, iters, n >> 16); }
 
 FMMT_API int fmmt_debug_feed(int iters, int nstage, int box_rows, int mode, int grid, double* out2) {
   return feed_probe(iters, nstage, box_rows, mode, grid, out2);
+}
+
+FMMT_API double fmmt_debug_feed2(int iters, int nstage, int box_rows, int pitch_elems, int nthr, int grid) {
+  return feed_probe2(iters, nstage, box_rows, pitch_elems, nthr, grid);
 }
 
 FMMT_API double fmmt_flops(fmmt_handle* h, int reset) { return h ? h->eng->flops(reset != 0) : 0.0; }

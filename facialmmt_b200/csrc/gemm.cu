@@ -281,7 +281,11 @@ constexpr int FAST_EPI_WARPS = 4 * EPI_GROUPS;
 constexpr int FAST_PRODUCER_WARP = FAST_EPI_WARPS;
 constexpr int FAST_MMA_WARP = FAST_EPI_WARPS + 1;
 constexpr int FAST_RES_WARP = FAST_EPI_WARPS + 2;
-constexpr int FAST_THREADS = (FAST_EPI_WARPS + 3) * 32;   // 608
+constexpr int FAST_PRODB_WARP = FAST_EPI_WARPS + 3;       // B-operand TMA producer: a second issuing thread, because one
+                                                           // thread's TMA stream is served one box at a time (~490 cycles
+                                                           // per box whatever its size; fmmt_debug_feed2) while streams of
+                                                           // different warps proceed in parallel
+constexpr int FAST_THREADS = (FAST_EPI_WARPS + 4) * 32;   // 640
 constexpr int SLAB_BYTES = 128 * 128;
 constexpr int RES_SLOTS = EPI_GROUPS;   // slot g is produced for / consumed by group g only
 
@@ -349,7 +353,7 @@ gemm_bf16_tcgen05_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __gr
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.num_stages; ++s) {
-      mbar_init(&full_bar[s], 1);
+      mbar_init(&full_bar[s], 2);     // A producer + B producer, each with its own expect_tx
       mbar_init(&empty_bar[s], 1);
     }
     for (int s = 0; s < 2; ++s) {
@@ -379,24 +383,37 @@ gemm_bf16_tcgen05_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __gr
   const int num_tiles = p.m_tiles * p.n_tiles;
 
   if (warp == FAST_PRODUCER_WARP) {
+    // ------------------------------------------------------------ A-operand TMA producer
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const int m0 = (tile / p.n_tiles) * BM;
-        const int n0 = (tile % p.n_tiles) * p.block_n;
         for (int kb = 0; kb < p.num_kb; kb += KBS) {
           mbar_wait(&empty_bar[stage], phase ^ 1u, 1);
           uint8_t* sa = pipe_gen + stage * p.stage_bytes;
-          uint8_t* sb = sa + KBS * A_TILE_BYTES;
-          mbar_arrive_expect_tx(&full_bar[stage], static_cast<uint32_t>(p.stage_bytes));
-          if (KBS > 1) {   // KBS k-blocks per instruction (3-D tensor maps; k-blocks past K are zero-filled)
-            tma_load_3d(sa, &tmA, &full_bar[stage], 0, m0, kb);
-            tma_load_3d(sb, &tmB, &full_bar[stage], 0, n0, kb);
-          } else {
-            tma_load_2d(sa, &tmA, &full_bar[stage], kb * BK, m0);
-            tma_load_2d(sb, &tmB, &full_bar[stage], kb * BK, n0);
-          }
+          mbar_arrive_expect_tx(&full_bar[stage], static_cast<uint32_t>(KBS * A_TILE_BYTES));
+          if (KBS > 1) tma_load_3d(sa, &tmA, &full_bar[stage], 0, m0, kb);   // KBS k-blocks in one instruction
+          else tma_load_2d(sa, &tmA, &full_bar[stage], kb * BK, m0);
+          if (++stage == p.num_stages) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == FAST_PRODB_WARP) {
+    // ------------------------------------------------------------ B-operand TMA producer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      const uint32_t b_bytes = static_cast<uint32_t>(p.block_n * BK * 2);
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int n0 = (tile % p.n_tiles) * p.block_n;
+        for (int kb = 0; kb < p.num_kb; kb += KBS) {
+          mbar_wait(&empty_bar[stage], phase ^ 1u, 1);
+          uint8_t* sb = pipe_gen + stage * p.stage_bytes + KBS * A_TILE_BYTES;
+          mbar_arrive_expect_tx(&full_bar[stage], KBS * b_bytes);
+#pragma unroll
+          for (int j = 0; j < KBS; ++j)   // k-blocks past K are zero-filled (and skipped by the MMA thread)
+            tma_load_2d(sb + j * b_bytes, &tmB, &full_bar[stage], (kb + j) * BK, n0);
           if (++stage == p.num_stages) { stage = 0; phase ^= 1u; }
         }
       }
@@ -565,7 +582,7 @@ gemm_bf16_tcgen05_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __gr
 // the K = 384 .. 4096 GEMMs of this path (operand feed from L2, see pick_block_n). The leader CTA's MMA thread issues
 // M = 256 instructions that read both CTAs' shared memory and write both CTAs' TMEM; every CTA runs its own TMA
 // producer, residual producer and epilogue for its 128 rows. Barriers:
-//   full_bar[s]   (leader's copy)  1 arrival (leader's producer) + the bytes of both CTAs' loads
+//   full_bar[s]   (leader's copy)  2 arrivals (the leader's A and B producers) + the bytes of both CTAs' loads
 //   empty_bar[s]  (each CTA)       1 arrival by tcgen05.commit multicast to the pair
 //   tmem_full[a]  (each CTA)       1 arrival by commit multicast;  tmem_empty[a] (leader's copy) all epilogue threads
 //                                  of BOTH CTAs (remote arrive through the shared::cluster window)
@@ -599,7 +616,7 @@ gemm_bf16_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __g
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.num_stages; ++s) {
-      mbar_init(&full_bar[s], 1);
+      mbar_init(&full_bar[s], 2);     // the leader's A and B producers (each expects the bytes of both CTAs' boxes)
       mbar_init(&empty_bar[s], 1);
     }
     for (int s = 0; s < 2; ++s) {
@@ -632,8 +649,11 @@ gemm_bf16_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __g
   const int pair_id = static_cast<int>(blockIdx.x >> 1);
   const int num_pairs = static_cast<int>(gridDim.x >> 1);
 
-  if (warp == FAST_PRODUCER_WARP) {
+  if (warp == FAST_PRODUCER_WARP || warp == FAST_PRODB_WARP) {
+    // ------------------------------------------------------------ TMA producers: one issuing thread per operand
     if (lane == 0) {
+      const bool is_a = warp == FAST_PRODUCER_WARP;
+      const uint32_t my_bytes = static_cast<uint32_t>(p.kbs) * (is_a ? A_TILE_BYTES : half_n * (BK * 2));
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = pair_id; tile < num_tiles; tile += num_pairs) {
@@ -643,15 +663,15 @@ gemm_bf16_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __g
           mbar_wait(&empty_bar[stage], phase ^ 1u, 1);
           uint8_t* sa = pipe_gen + stage * p.stage_bytes;
           const uint32_t lead_full = mapa_u32(smem_u32(&full_bar[stage]), 0);
-          // one arrival (the leader's) + the bytes of both CTAs: the peer only refills a slot after the commit that
-          // followed the leader's wait on the slot's previous phase, so its bytes always land in the right phase
-          if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2u * static_cast<uint32_t>(p.stage_bytes));
+          // arrivals come from the leader only; the peer's bytes always land in the right phase because the peer refills
+          // a slot only after the commit that followed the leader's wait on the slot's previous phase
+          if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2u * my_bytes);
           if (p.kbs > 1) {   // one instruction per operand: kbs k-blocks (past K: zero-filled, skipped by the MMA thread)
-            tma_load_3d_pair(sa, &tmA, lead_full, 0, m0, kb);
-            tma_load_3d_pair(sa + p.kbs * A_TILE_BYTES, &tmB, lead_full, 0, nb0, kb);
+            if (is_a) tma_load_3d_pair(sa, &tmA, lead_full, 0, m0, kb);
+            else tma_load_3d_pair(sa + p.kbs * A_TILE_BYTES, &tmB, lead_full, 0, nb0, kb);
           } else {
-            tma_load_2d_pair(sa, &tmA, lead_full, kb * BK, m0);
-            tma_load_2d_pair(sa + A_TILE_BYTES, &tmB, lead_full, kb * BK, nb0);
+            if (is_a) tma_load_2d_pair(sa, &tmA, lead_full, kb * BK, m0);
+            else tma_load_2d_pair(sa + A_TILE_BYTES, &tmB, lead_full, kb * BK, nb0);
           }
           if (++stage == p.num_stages) { stage = 0; phase ^= 1u; }
         }
@@ -812,14 +832,19 @@ gemm_bf16_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __g
 // ---------------------------------------------------------------- tensor-pipe probe (test/bench only)
 // One CTA per SM issues `iters` x 4 MMAs (M = 128, N = n, K = 16 each) on the same shared-memory tiles, with no TMA
 // traffic at all, and reports the cycles of the slowest CTA: the MMA issue/execute floor of this part.
-__global__ void __launch_bounds__(128, 1) mma_rate_probe_kernel(int n, int iters, long long* cycles_out) {
+__global__ void __launch_bounds__(128, 1) mma_rate_probe_kernel(int n, int iters, int mode, long long* cycles_out) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ uint64_t done_bar;
+  __shared__ uint64_t stage_bar[4];
   __shared__ uint32_t tmem_base_slot;
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem = smem_raw + (smem_base - smem_u32(smem_raw));
-  for (int i = threadIdx.x; i < (A_TILE_BYTES + 256 * 128) / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem)[i] = 0x3c003c00u;
-  if (threadIdx.x == 0) { mbar_init(&done_bar, 1); fence_barrier_init(); }
+  for (int i = threadIdx.x; i < 2 * (A_TILE_BYTES + 256 * 128) / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem)[i] = 0x3c003c00u;
+  if (threadIdx.x == 0) {
+    mbar_init(&done_bar, 1);
+    for (int s = 0; s < 4; ++s) mbar_init(&stage_bar[s], 1);
+    fence_barrier_init();
+  }
   if (threadIdx.x < 32) { tmem_alloc(&tmem_base_slot, TMEM_COLS); tmem_relinquish(); }
   fence_proxy_async_smem();
   tc_fence_before();
@@ -827,14 +852,20 @@ __global__ void __launch_bounds__(128, 1) mma_rate_probe_kernel(int n, int iters
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_slot;
   if (threadIdx.x == 0) {
+    // mode bit 0: tcgen05.commit to a barrier after every 4 MMAs (as the GEMM releases a pipeline stage)
+    // mode bit 1: tcgen05.fence::after_thread_sync before every 4 MMAs;  mode bit 2: alternate two operand tile sets
     const uint32_t idesc = make_idesc_bf16(BM, n);
-    const uint64_t adesc = make_smem_desc_sw128(smem_base);
-    const uint64_t bdesc = make_smem_desc_sw128(smem_base + A_TILE_BYTES);
     const long long t0 = clock64();
-    for (int it = 0; it < iters; ++it)
+    for (int it = 0; it < iters; ++it) {
+      const uint32_t off = (mode & 4) ? static_cast<uint32_t>(it & 1) * (A_TILE_BYTES + 256 * 128) : 0u;
+      const uint64_t adesc = make_smem_desc_sw128(smem_base + off);
+      const uint64_t bdesc = make_smem_desc_sw128(smem_base + off + A_TILE_BYTES);
+      if (mode & 2) tc_fence_after();
       for (int k = 0; k < 4; ++k)
         umma_bf16(tmem_base + static_cast<uint32_t>((it & 1) * ACC_STRIDE), adesc + static_cast<uint64_t>(2 * k),
                   bdesc + static_cast<uint64_t>(2 * k), idesc, (it | k) > 1 ? 1u : 0u);
+      if (mode & 1) umma_commit(&stage_bar[it & 3]);
+    }
     umma_commit(&done_bar);
     mbar_wait(&done_bar, 0, 7);
     const long long t1 = clock64();
@@ -844,7 +875,6 @@ __global__ void __launch_bounds__(128, 1) mma_rate_probe_kernel(int n, int iters
   __syncthreads();
   if (threadIdx.x < 32) { tc_fence_after(); tmem_dealloc(tmem_base, TMEM_COLS); }
 }
-
 
 // Feed probe (bench only): every CTA streams `iters` boxes of 64 x box_rows bf16 (SWIZZLE_128B) from an L2-resident
 // matrix through `nstage` shared-memory slots with TMA; mode 1 additionally keeps the tensor pipe busy with N = 256
@@ -904,6 +934,43 @@ feed_probe_kernel(const __grid_constant__ CUtensorMap tm, int iters, int nstage,
   tc_fence_before();
   __syncthreads();
   if (threadIdx.x < 32) { tc_fence_after(); tmem_dealloc(tmem_base, TMEM_COLS); }
+}
+
+
+// Feed probe 2 (bench only): `nthr` issuing threads (one per warp), each streaming `iters` boxes of 64 x box_rows bf16 from
+// its own row range of an L2-resident matrix with row pitch `pitch_elems`, `nstage` boxes in flight per thread.
+__global__ void __launch_bounds__(128, 1)
+feed_probe2_kernel(const __grid_constant__ CUtensorMap tm, int iters, int nstage, int box_rows, int rows_total, int nthr,
+                   long long* cycles_out) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ uint64_t full[4][MAX_STAGES];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + (smem_base - smem_u32(smem_raw));
+  const int box_bytes = box_rows * 128;
+  if (threadIdx.x == 0) {
+    for (int t = 0; t < 4; ++t)
+      for (int s = 0; s < nstage; ++s) mbar_init(&full[t][s], 1);
+    fence_barrier_init();
+  }
+  __syncthreads();
+  const int w = threadIdx.x >> 5;
+  if ((threadIdx.x & 31) == 0 && w < nthr) {
+    const int nblk = rows_total / box_rows;
+    int blk = (blockIdx.x * 37 + w * 101) % nblk;
+    uint8_t* base = smem + w * nstage * box_bytes;
+    const long long t0 = clock64();
+    for (int it = 0; it < iters + nstage; ++it) {
+      const int s = it % nstage;
+      if (it >= nstage) mbar_wait(&full[w][s], ((it / nstage) - 1) & 1u, 8);
+      if (it < iters) {
+        mbar_arrive_expect_tx(&full[w][s], box_bytes);
+        tma_load_2d(base + s * box_bytes, &tm, &full[w][s], 0, blk * box_rows);
+        blk = blk + 1 == nblk ? 0 : blk + 1;
+      }
+    }
+    const long long t1 = clock64();
+    atomicMax(reinterpret_cast<unsigned long long*>(cycles_out), static_cast<unsigned long long>(t1 - t0));
+  }
 }
 
 // ---------------------------------------------------------------- host side
@@ -1126,16 +1193,16 @@ bool make_tmap_kblocks_2d(CUtensorMap* tm, const void* base, long long rows, lon
   return make_tmap_kblocks(tm, base, rows, K, ld_elems, box_rows, box_kb);
 }
 
-double mma_rate_probe(int n, int iters) {
+double mma_rate_probe(int n, int iters, int mode) {
   long long* d = nullptr;
   if (cudaMalloc(&d, sizeof(long long)) != cudaSuccess) return -1.0;
   cudaMemset(d, 0, sizeof(long long));
-  const size_t smem = A_TILE_BYTES + 256 * 128 + 1024;
+  const size_t smem = 2 * (A_TILE_BYTES + 256 * 128) + 1024;
   cudaFuncSetAttribute(mma_rate_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  mma_rate_probe_kernel<<<sms, 128, smem>>>(n, iters, d);
+  mma_rate_probe_kernel<<<sms, 128, smem>>>(n, iters, mode, d);
   long long h = 0;
   cudaError_t e = cudaMemcpy(&h, d, sizeof(h), cudaMemcpyDeviceToHost);
   cudaFree(d);
@@ -1173,6 +1240,35 @@ int feed_probe(int iters, int nstage, int box_rows, int mode, int grid, double* 
   cudaFree(buf);
   cudaFree(d);
   return rc;
+}
+
+double feed_probe2(int iters, int nstage, int box_rows, int pitch_elems, int nthr, int grid) {
+  if (nstage < 1 || nstage > MAX_STAGES || box_rows < 8 || box_rows > 256 || nthr < 1 || nthr > 4 || pitch_elems < 64) return -1.0;
+  const size_t bytes = static_cast<size_t>(64) << 20;   // 64 MB: L2-resident after the first pass
+  const int rows_total = static_cast<int>(bytes / (static_cast<size_t>(pitch_elems) * 2));
+  __nv_bfloat16* buf = nullptr;
+  long long* d = nullptr;
+  if (cudaMalloc(&buf, bytes) != cudaSuccess) return -1.0;
+  cudaMemset(buf, 0, bytes);
+  cudaMalloc(&d, sizeof(long long));
+  double out = -1.0;
+  CUtensorMap tm;
+  if (make_tmap(&tm, buf, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, rows_total, 64, pitch_elems, 64, box_rows)) {
+    const size_t smem = static_cast<size_t>(nthr) * nstage * box_rows * 128 + 1024;
+    if (smem <= static_cast<size_t>(SMEM_BUDGET + 1024)) {
+      cudaFuncSetAttribute(feed_probe2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+      for (int rep = 0; rep < 2; ++rep) {
+        cudaMemset(d, 0, sizeof(long long));
+        feed_probe2_kernel<<<grid, 128, smem>>>(tm, iters, nstage, box_rows, rows_total, nthr, d);
+      }
+      long long h = 0;
+      if (cudaMemcpy(&h, d, sizeof(h), cudaMemcpyDeviceToHost) == cudaSuccess && h > 0)
+        out = static_cast<double>(iters) * nthr * box_rows * 128 / static_cast<double>(h);
+    }
+  }
+  cudaFree(buf);
+  cudaFree(d);
+  return out;
 }
 
 unsigned int read_mbar_timeout(bool reset) {
@@ -1278,11 +1374,10 @@ cudaError_t launch_gemm(const GemmArgs& a, cudaStream_t stream) {
     CUtensorMap tmRes, tmOut;
     if (use3d) {
       if (!make_tmap_kblocks(&tmA, a.A, a.M, a.K, a.lda, BM, 2)) return cudaErrorInvalidValue;
-      if (!make_tmap_kblocks(&tmB, a.W, a.N, a.K, a.ldw, p.block_n, 2)) return cudaErrorInvalidValue;
     } else {
       if (!make_tmap(&tmA, a.A, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, a.M, a.K, a.lda, BK, BM)) return cudaErrorInvalidValue;
-      if (!make_tmap(&tmB, a.W, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, a.N, a.K, a.ldw, BK, p.block_n)) return cudaErrorInvalidValue;
     }
+    if (!make_tmap(&tmB, a.W, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, a.N, a.K, a.ldw, BK, p.block_n)) return cudaErrorInvalidValue;
     if (p.out_bf16) {
       if (!make_tmap(&tmOut, a.out_bf16, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, a.M, a.N, a.ldo16, 64, BM)) return cudaErrorInvalidValue;
     } else {

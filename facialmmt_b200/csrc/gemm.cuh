@@ -56,11 +56,14 @@ unsigned int read_mbar_timeout(bool reset);
 
 // Tensor-pipe probe (bench only): cycles per tcgen05.mma (M = 128, N = n, K = 16, bf16) with operands resident in
 // shared memory and no other traffic; all SMs run it at once. Synchronous.
-double mma_rate_probe(int n, int iters);
+double mma_rate_probe(int n, int iters, int mode = 0);
 
 // Feed probe (bench only): TMA bytes per cycle per SM from an L2-resident matrix (out2[0]) with `nstage` boxes of
 // 64 x box_rows bf16 in flight on `grid` CTAs; mode 1 runs N = 256 MMAs beside it and reports cycles per MMA (out2[1]).
 int feed_probe(int iters, int nstage, int box_rows, int mode, int grid, double* out2);
+
+// Feed probe 2: bytes per cycle per SM with `nthr` independent TMA streams and a row pitch of `pitch_elems` bf16.
+double feed_probe2(int iters, int nstage, int box_rows, int pitch_elems, int nthr, int grid);
 
 // Algorithmic work of one launch (2*M*N*K) for roofline accounting.
 inline double gemm_flops(const GemmArgs& a) { return 2.0 * a.M * (double)a.N * a.K; }

@@ -127,11 +127,15 @@ FMMT_API int64_t fmmt_profile_read(fmmt_handle* h, char* buf, int64_t buf_len);
  * 0-11 thread. Synchronises the device. */
 FMMT_API uint32_t fmmt_debug_timeout(int reset);
 /* Bench probe: cycles per tcgen05.mma (M=128, N=n, K=16, bf16) issued back to back on resident shared-memory tiles, all
- * SMs at once (the tensor-pipe floor the GEMM roofline fractions are read against). Synchronous. */
+ * SMs at once (the tensor-pipe floor the GEMM roofline fractions are read against). Bits 16.. of n select a variant:
+ * 1 = tcgen05.commit after every 4 MMAs, 2 = tcgen05.fence before every 4, 4 = alternate two operand tile sets. Synchronous. */
 FMMT_API double fmmt_debug_mma_cycles(int n, int iters);
 /* Bench probe: TMA feed rate from L2 (out2[0] = bytes per cycle per SM) with `nstage` 64 x box_rows bf16 boxes in flight on
  * `grid` CTAs; mode 1 keeps the tensor pipe busy beside it and reports cycles per N=256 MMA in out2[1]. Synchronous. */
 FMMT_API int fmmt_debug_feed(int iters, int nstage, int box_rows, int mode, int grid, double* out2);
+/* Bench probe 2: same with `nthr` (1..4) independent issuing threads and a matrix row pitch of `pitch_elems` bf16
+ * (64 = boxes contiguous in memory); returns bytes per cycle per SM. Synchronous. */
+FMMT_API double fmmt_debug_feed2(int iters, int nstage, int box_rows, int pitch_elems, int nthr, int grid);
 /* Algorithmic FLOPs (2*MAC of every GEMM/attention launched) accumulated by the handle since the last reset. */
 FMMT_API double fmmt_flops(fmmt_handle* h, int reset);
 /* Bytes of device memory held by the handle (weights + workspace). */
