@@ -36,7 +36,9 @@ constexpr int LN_WARPS = 8;
 constexpr int MMA_WARP = LN_WARP0 + LN_WARPS;  // warp 24
 constexpr int PROD1_WARP = MMA_WARP + 1;       // warp 25: fc1 weight stream
 constexpr int PROD2_WARP = MMA_WARP + 2;       // warp 26: fc2 weight stream
-constexpr int THREADS = (PROD2_WARP + 1) * 32; // 864
+constexpr int PROD3_WARP = MMA_WARP + 3;       // warp 27: fc1 weight stream, odd pieces (one TMA stream per piece slot:
+                                               //   a single thread's boxes are served one at a time, fmmt_debug_feed2)
+constexpr int THREADS = (PROD3_WARP + 1) * 32; // 896
 constexpr int DRAIN_STREAMS = 3;               // GELU warps 0..11, four warps (128 rows) per stream
 
 template <int C>
@@ -137,14 +139,16 @@ swin_mlp_stream_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_co
                       static_cast<int>(gridDim.x);
   const int copy = static_cast<int>(blockIdx.x) % p.copies;
 
-  if (warp == PROD1_WARP) {
-    // ------------------------------------------------------------------ fc1 weight stream (one thread)
+  if (warp == PROD1_WARP || warp == PROD3_WARP) {
+    // ------------------------------------------------------------------ fc1 weight streams (one thread per piece slot)
     if (lane == 0) {
+      const uint32_t mine = warp == PROD1_WARP ? 0u : 1u;
       uint32_t u = 0;   // running piece number of this CTA: slot u & 1, use u >> 1
       for (int i = 0; i < n_local; ++i)
         for (int j = 0; j < K::CHUNKS; ++j)
           for (int pc = 0; pc < K::PIECES; ++pc, ++u) {
             const uint32_t sl = u & 1u;
+            if (sl != mine) continue;
             mbar_wait(&w1_empty[sl], ((u >> 1) & 1u) ^ 1u, 40);      // the MMAs on this slot's previous piece are done
             if (p.trace != nullptr && blockIdx.x == 0 && i == 0 && pc == 0) p.trace[j * 8 + 5] = clock64();   // piece 0 requested
             mbar_arrive_expect_tx(&w1_full[sl], K::W1_PIECE);
