@@ -808,8 +808,10 @@ void Engine::swin_body(const float* frames, int F, const float* gumbel, float ta
   const size_t FL = static_cast<size_t>(sl.R) * sl.R * sl.C;
   bf16* feat_ln = arena_.alloc<bf16>(static_cast<size_t>(F) * FL);
   float* feat512 = arena_.alloc<float>(static_cast<size_t>(F) * c.feat_dim);
-  const int big = c.swin_chunk_late > 0 ? c.swin_chunk_late : 160;   // measured best on B200 (profiles/)
-  const int small = c.swin_chunk > 0 ? c.swin_chunk : 64;
+  // Frames per pass: measured on B200 (profiles/r01_chunk_sweep.txt). With persistent kernels bigger passes win (fewer
+  // launches, fewer partial waves): 64/160 -> 196 utt/s, 96/192 -> 217, 320/640 -> 234, 320/1280 -> 239, 1280/1280 -> 236.
+  const int big = c.swin_chunk_late > 0 ? c.swin_chunk_late : 1280;
+  const int small = c.swin_chunk > 0 ? c.swin_chunk : 320;
   const SwinStageW& ss = swin_.stages[split];
   const size_t per_frame_split = static_cast<size_t>(ss.R) * ss.R * ss.C;
   for (int f0 = 0; f0 < F; f0 += big) {
