@@ -50,13 +50,8 @@ def build_parser():
 
 
 def _load_sd(path):
-    obj = torch.load(path, map_location="cpu", weights_only=False)
-    if hasattr(obj, "state_dict"):
-        obj = obj.state_dict()
-    if isinstance(obj, dict) and "state_dict" in obj:
-        obj = obj["state_dict"]
-    # strip wrappers the reference's pickles carry (_LiteModule -> DataParallel -> module)
-    return {k.replace("_module.", "").replace("module.", ""): v for k, v in obj.items()}
+    from facialmmt_b200.checkpoint import load_state_dict_file
+    return load_state_dict_file(path)
 
 
 def main(argv=None):

@@ -98,3 +98,36 @@ def test_cli_keeps_reference_flag_names():
     a = cli.build_parser().parse_args(["--choice_modality", "T+A+V", "--plm_name", "bert-large", "--doEval", "1",
                                        "--FacialEmoImpor_threshold", "0.25", "--tau", "2", "--trg_batch_size", "4"])
     assert a.plm_name == "bert-large" and a.FacialEmoImpor_threshold == 0.25 and a.tau == 2 and a.trg_batch_size == 4
+
+
+def test_checkpoint_ingestion_wrappers_and_backbone_remap(tmp_path):
+    """train.py:428-432 pickles (_LiteModule -> DataParallel -> module) and the backbone.* remap of train.py:316-331."""
+    import torch
+    from facialmmt_b200.checkpoint import load_state_dict_file, remap_pretrained_backbone, strip_wrappers, to_state_dict
+
+    inner = torch.nn.Sequential(torch.nn.Linear(3, 2))
+    wrapped = torch.nn.Sequential()
+    wrapped.add_module("_module", torch.nn.Sequential())
+    wrapped._module.add_module("module", inner)                      # keys: _module.module.0.weight
+    assert set(to_state_dict(wrapped)) == {"0.weight", "0.bias"}
+    assert set(strip_wrappers({"module._module.module.a.b": 1})) == {"a.b"}
+    p = tmp_path / "sd.pt"
+    torch.save({"state_dict": {"module.linear.weight": torch.ones(2, 2)}}, p)
+    assert set(load_state_dict_file(str(p))) == {"linear.weight"}
+    with pytest.raises(TypeError):
+        to_state_dict(3)
+
+    model_keys = ["swin.patch_embed.proj.weight", "linear.weight", "classifier.weight", "classifier.bias", "swin.missing"]
+    pre = {"backbone.patch_embed.proj.weight": torch.zeros(1), "backbone.linear.weight": torch.ones(1),
+           "backbone.classifier.weight": torch.ones(1), "linear.weight": torch.full((1,), 2.0)}
+    got = remap_pretrained_backbone(model_keys, pre)
+    assert set(got) == {"swin.patch_embed.proj.weight", "linear.weight"} and got["linear.weight"].item() == 1.0
+    # the literal reference loop, restated verbatim, agrees with literal=True
+    ref = {}
+    for k in model_keys:
+        if k in pre:
+            if k == 'classifier.weight' or k == 'classifier.bias':
+                continue
+            k_val = k[5:] if k[:5] == 'swin.' else k
+            ref[k] = pre['backbone.' + k_val]
+    assert set(remap_pretrained_backbone(model_keys, pre, literal=True)) == set(ref) == {"linear.weight"}
