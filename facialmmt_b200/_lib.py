@@ -54,6 +54,7 @@ SIGNATURES = {
                                  c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "fmmt_multimodal_forward": (c_int, [c_void_p] * 9 + [c_int, c_int, c_void_p, c_void_p]),
     "fmmt_unimodal_forward": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
+    "fmmt_check": (c_int, [c_void_p]),
     "fmmt_set_capture": (c_int, [c_void_p, c_char_p, c_void_p, c_int64]),
     "fmmt_set_profile": (c_int, [c_void_p, c_int]),
     "fmmt_profile_read": (c_int64, [c_void_p, c_void_p, c_int64]),
@@ -73,6 +74,8 @@ SIGNATURES = {
     "fmmt_op_swin_mlp": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_float, c_void_p, c_void_p, c_void_p, c_void_p]),
     "fmmt_op_swin_mlp_stream": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_float, c_void_p, c_int, c_void_p,
                                         c_void_p, c_int, c_void_p, c_int, c_void_p]),
+    "fmmt_op_span_extract": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p,
+                                     c_void_p]),
     "fmmt_op_mha": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_void_p, c_float,
                             c_int, c_int, c_int, c_int, c_float, c_void_p]),
 }

@@ -408,6 +408,8 @@ __global__ void __launch_bounds__(128) mha_flash_kernel(const MhaParams p) {
 
 }  // namespace
 
+FMMT_DEFINE_WATCHDOG_ADDR(watchdog_addr_attn)
+
 cudaError_t launch_window_attention(const __nv_bfloat16* qkv, __nv_bfloat16* out, const float* bias,
                                     const int8_t* rid, int num_windows, int nW, int heads, int C, int N, float scale,
                                     cudaStream_t stream) {

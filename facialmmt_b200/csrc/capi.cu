@@ -96,6 +96,11 @@ FMMT_API int fmmt_unimodal_forward(fmmt_handle* h, const float* inputs, const fl
   return h->eng->unimodal_forward(inputs, utt_mask, U, logits, S(stream));
 }
 
+FMMT_API int fmmt_check(fmmt_handle* h) {
+  if (!h) return set_error(FMMT_ERR_INVALID, "null handle");
+  return h->eng->check();
+}
+
 FMMT_API int fmmt_set_capture(fmmt_handle* h, const char* name, float* dst, int64_t count) {
   if (!h) return set_error(FMMT_ERR_INVALID, "null handle");
   return h->eng->set_capture(name, dst, count);
@@ -229,6 +234,16 @@ FMMT_API int fmmt_op_mha(const void* q, int ldq, const void* k, int ldk, const v
                                static_cast<const __nv_bfloat16*>(v), ldv, static_cast<__nv_bfloat16*>(out), ldo, key_mask,
                                mask_neg, B, H, Lq, Lk, scale, S(stream)),
                     "fmmt_op_mha");
+}
+
+FMMT_API int fmmt_op_span_extract(const float* text, const int64_t* sep_mask, const int64_t* idx_in_dia, int U, int L,
+                                  int H, int max_len, int text_kind, float* out, float* out_mask, void* stream) {
+  if (!text || !sep_mask || !idx_in_dia || !out || !out_mask) return set_error(FMMT_ERR_INVALID, "fmmt_op_span_extract: null pointer");
+  if (text_kind != FMMT_TEXT_ROBERTA && text_kind != FMMT_TEXT_BERT) return set_error(FMMT_ERR_INVALID, "fmmt_op_span_extract: text_kind");
+  count_launch();
+  return check_cuda(launch_span_extract(text, sep_mask, idx_in_dia, U, L, H, max_len, text_kind == FMMT_TEXT_ROBERTA ? 2 : 1,
+                                        out, out_mask, S(stream)),
+                    "fmmt_op_span_extract");
 }
 
 }  // extern "C"

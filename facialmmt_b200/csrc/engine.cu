@@ -35,6 +35,7 @@ Engine::~Engine() {
   for (cudaEvent_t e : ev_pool_) cudaEventDestroy(e);
   for (void* p : dev_ptrs_) cudaFree(p);
   if (ws_) cudaFree(ws_);
+  if (status_host_) cudaFreeHost(status_host_);
 }
 
 int Engine::load_weight(const char* key, const float* data, const int64_t* shape, int ndim) {
@@ -467,9 +468,39 @@ int Engine::finalize() {
   }
   cudaError_t e = cudaDeviceSynchronize();
   if (e != cudaSuccess) return set_error(FMMT_ERR_CUDA, std::string("fmmt_finalize: ") + cudaGetErrorString(e));
+  cudaGetDevice(&device_);
+  try {
+    status_dev_ = dev_alloc<unsigned int>(1);
+  } catch (const PackError& pe) {
+    return set_error(FMMT_ERR_CUDA, std::string("fmmt_finalize: ") + pe.what());
+  }
+  cudaMemset(status_dev_, 0, sizeof(unsigned int));
+  if (cudaMallocHost(reinterpret_cast<void**>(&status_host_), sizeof(unsigned int)) != cudaSuccess)
+    return set_error(FMMT_ERR_CUDA, "fmmt_finalize: cudaMallocHost(status word) failed");
+  *status_host_ = 0;
   host_.clear();
   finalized_ = true;
   return FMMT_OK;
+}
+
+int Engine::consume_status(const char* where) {
+  if (status_host_ == nullptr) return FMMT_OK;
+  const unsigned int v = *reinterpret_cast<volatile unsigned int*>(status_host_);
+  if (v == 0) return FMMT_OK;
+  *status_host_ = 0;
+  char buf[256];
+  snprintf(buf, sizeof(buf),
+           "%s: the pipeline watchdog fired in an earlier forward on this handle (mbarrier wait timed out: barrier tag %u, "
+           "CTA %u, thread %u); the results of that forward are invalid",
+           where, (v >> 24) & 0x7Fu, (v >> 12) & 0xFFFu, v & 0xFFFu);
+  return set_error(FMMT_ERR_CUDA, buf);
+}
+
+int Engine::check() {
+  if (!finalized_) return set_error(FMMT_ERR_STATE, "handle is not finalized (call fmmt_finalize)");
+  cudaError_t e = cudaStreamSynchronize(st_);
+  if (e != cudaSuccess) return set_error(FMMT_ERR_CUDA, std::string("fmmt_check: ") + cudaGetErrorString(e));
+  return consume_status("fmmt_check");
 }
 
 int Engine::set_capture(const char* name, float* dst, int64_t count) {
@@ -626,6 +657,10 @@ void Engine::capture(const std::string& name, const float* src, size_t count, si
 template <typename Fn>
 int Engine::run(Fn&& body, cudaStream_t st) {
   if (!finalized_) return set_error(FMMT_ERR_STATE, "handle is not finalized (call fmmt_finalize)");
+  int dev = -1;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev != device_)
+    return set_error(FMMT_ERR_STATE, "the current CUDA device is not the one this handle was finalized on (one handle per device)");
+  if (int rc = consume_status("forward")) return rc;
   st_ = st;
   first_err_ = cudaSuccess;
   err_.clear();
@@ -646,6 +681,13 @@ int Engine::run(Fn&& body, cudaStream_t st) {
   }
   arena_.begin(false, ws_, ws_cap_);
   body();
+  {
+    // pipeline watchdog hand-off: collect + clear the per-translation-unit words, copy to the pinned status word
+    unsigned int* addrs[4] = {watchdog_addr_gemm(), watchdog_addr_mlp96(), watchdog_addr_mlp_stream(), watchdog_addr_attn()};
+    count_launch();
+    ck(launch_collect_status(addrs, 4, status_dev_, st_), "collect_status");
+    ck(cudaMemcpyAsync(status_host_, status_dev_, sizeof(unsigned int), cudaMemcpyDeviceToHost, st_), "status copy");
+  }
   if (first_err_ != cudaSuccess) return set_error(first_err_ == cudaErrorInvalidValue ? FMMT_ERR_INVALID : FMMT_ERR_CUDA, err_);
   return FMMT_OK;
 }

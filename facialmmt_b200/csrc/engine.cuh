@@ -150,6 +150,9 @@ class Engine {
   // Per-kernel CUDA-event timing (on the launch stream) for roofline accounting; adds two event records per launch.
   void set_profile(bool on);
   std::string profile_json();  // synchronises; aggregates by kernel key since set_profile(true)
+  // Synchronises the stream of the last forward and reports a pipeline-watchdog event (ptx.cuh) of any forward since
+  // the previous check: FMMT_OK or FMMT_ERR_CUDA (message via fmmt_last_error). Clears the condition.
+  int check();
   double flops(bool reset) { double f = flops_; if (reset) flops_ = 0; return f; }
   int64_t device_bytes() const { return static_cast<int64_t>(weight_bytes_ + ws_cap_); }
   const std::string& error() const { return err_; }
@@ -218,6 +221,10 @@ class Engine {
   float* sinusoid_ = nullptr;  // [max_len+1, H]
   int sinusoid_len_ = 0;
 
+  int device_ = -1;                       // the device that owns the weights and the workspace (set by finalize)
+  unsigned int* status_dev_ = nullptr;    // device word written by launch_collect_status at the end of every forward
+  unsigned int* status_host_ = nullptr;   // pinned copy (stream-ordered D2H at the end of every forward)
+  int consume_status(const char* where);  // FMMT_ERR_CUDA if the pinned word is set (and clears it)
   Arena arena_;
   char* ws_ = nullptr;
   size_t ws_cap_ = 0;

@@ -1271,6 +1271,8 @@ double feed_probe2(int iters, int nstage, int box_rows, int pitch_elems, int nth
   return out;
 }
 
+FMMT_DEFINE_WATCHDOG_ADDR(watchdog_addr_gemm)
+
 unsigned int read_mbar_timeout(bool reset) {
   unsigned int v = 0;
   cudaMemcpyFromSymbol(&v, g_mbar_timeout, sizeof(v));

@@ -68,4 +68,7 @@ double feed_probe2(int iters, int nstage, int box_rows, int pitch_elems, int nth
 // Algorithmic work of one launch (2*M*N*K) for roofline accounting.
 inline double gemm_flops(const GemmArgs& a) { return 2.0 * a.M * (double)a.N * a.K; }
 
+// device address of this translation unit's pipeline-watchdog word (ptx.cuh)
+unsigned int* watchdog_addr_gemm();
+
 }  // namespace fmmt

@@ -539,6 +539,19 @@ __global__ void cast_i64_f32_kernel(const int64_t* __restrict__ in, float* __res
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) out[i] = static_cast<float>(in[i]);
 }
 
+// Pipeline-watchdog hand-off (ptx.cuh): OR every translation unit's word into *out and clear the words.
+struct WatchdogAddrs { unsigned int* a[8]; int n; };
+__global__ void collect_status_kernel(const WatchdogAddrs w, unsigned int* __restrict__ out) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  unsigned int v = 0;
+  for (int i = 0; i < w.n; ++i)
+    if (w.a[i] != nullptr) {
+      const unsigned int x = atomicExch(w.a[i], 0u);
+      if (v == 0) v = x;
+    }
+  *out = v;
+}
+
 inline int grid_for(long long n, int block, int cap = 148 * 16) {
   long long g = (n + block - 1) / block;
   if (g > cap) g = cap;
@@ -654,6 +667,15 @@ cudaError_t launch_gather_rows(const float* in, const int* map, int period, int 
   if (M <= 0 || (C % 4) != 0 || period <= 0) return cudaErrorInvalidValue;
   const long long total4 = static_cast<long long>(M) * (C / 4);
   gather_rows_kernel<<<grid_for(total4, 256), 256, 0, stream>>>(in, map, period, C / 4, total4, out);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_collect_status(unsigned int* const* addrs, int n, unsigned int* out, cudaStream_t stream) {
+  if (n < 0 || n > 8 || out == nullptr) return cudaErrorInvalidValue;
+  WatchdogAddrs w{};
+  w.n = n;
+  for (int i = 0; i < n; ++i) w.a[i] = addrs[i];
+  collect_status_kernel<<<1, 32, 0, stream>>>(w, out);
   return cudaGetLastError();
 }
 

@@ -395,6 +395,8 @@ void mlp96_pack_weights(const float* fc1_w, const float* fc2_w, __nv_bfloat16* i
         put(OFF_W2 + static_cast<size_t>(c) * 12288 + sw128_off(n, k), fc2_w[static_cast<size_t>(n) * MLP96_H + 64 * c + k]);
 }
 
+FMMT_DEFINE_WATCHDOG_ADDR(watchdog_addr_mlp96)
+
 unsigned int read_mlp_timeout(bool reset) {
   unsigned int v = 0;
   cudaMemcpyFromSymbol(&v, g_mbar_timeout, sizeof(v));

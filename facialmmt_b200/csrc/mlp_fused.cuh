@@ -30,4 +30,7 @@ inline double mlp96_flops(int M) { return 2.0 * 2.0 * M * (double)MLP96_C * MLP9
 // same contract as read_mbar_timeout (gemm.cuh) for the barriers of this translation unit; tags 16..31
 unsigned int read_mlp_timeout(bool reset);
 
+// device address of this translation unit's pipeline-watchdog word (ptx.cuh)
+unsigned int* watchdog_addr_mlp96();
+
 }  // namespace fmmt

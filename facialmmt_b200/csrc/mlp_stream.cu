@@ -448,6 +448,8 @@ cudaError_t launch_c(const MlpStreamArgs& a, cudaStream_t stream) {
 
 }  // namespace
 
+FMMT_DEFINE_WATCHDOG_ADDR(watchdog_addr_mlp_stream)
+
 unsigned int read_mlp_stream_timeout(bool reset) {
   unsigned int v = 0;
   cudaMemcpyFromSymbol(&v, g_mbar_timeout, sizeof(v));

@@ -31,4 +31,7 @@ inline double mlp_stream_flops(int M, int C) { return 2.0 * 2.0 * M * (double)C 
 // same contract as read_mbar_timeout (gemm.cuh) for the barriers of this translation unit; tags 40..52
 unsigned int read_mlp_stream_timeout(bool reset);
 
+// device address of this translation unit's pipeline-watchdog word (ptx.cuh)
+unsigned int* watchdog_addr_mlp_stream();
+
 }  // namespace fmmt

@@ -14,6 +14,8 @@ cudaError_t launch_mha(const __nv_bfloat16* q, int ldq, const __nv_bfloat16* k, 
                        int ldv, __nv_bfloat16* out, int ldo, const float* key_mask, float mask_neg, int B, int H,
                        int Lq, int Lk, float scale, cudaStream_t stream);
 
+unsigned int* watchdog_addr_attn();   // device address of attention.cu's pipeline-watchdog word (ptx.cuh)
+
 // ---- kernels.cu
 // LayerNorm over rows assembled from `nseg` source segments of `cseg` channels each (C = nseg*cseg <= 1536):
 //   out row r, segment s comes from source row  (r / map_period) * src_period + map[(r % map_period) * nseg + s]
@@ -81,6 +83,8 @@ cudaError_t launch_pool_classify(const float* x, const __nv_bfloat16* th, const 
 // out[q*period + t] = in[q*period + map[t]] for rows of C floats (parity captures of permuted activations)
 cudaError_t launch_gather_rows(const float* in, const int* map, int period, int C, int M, float* out,
                                cudaStream_t stream);
+// Pipeline watchdog (ptx.cuh): *out = first non-zero of the `n` per-translation-unit words, which are cleared.
+cudaError_t launch_collect_status(unsigned int* const* addrs, int n, unsigned int* out, cudaStream_t stream);
 cudaError_t launch_cast_i64_f32(const int64_t* in, float* out, int n, cudaStream_t stream);
 
 // Concatenate 0/1 masks along time: out[u] = [a[u] | b[u] | c[u]]

@@ -42,10 +42,20 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return done != 0;
 }
-// Bounded spin: a protocol bug must never hang the GPU. On timeout the waiter records who it was in a global word
-// (read back through fmmt_debug_timeout()) and every other waiter bails out as soon as it sees the word set, so the
-// kernel terminates (with wrong results) and the host reports the failure.
+// Bounded spin: a protocol bug must never hang the GPU. On timeout the waiter records who it was in a global word and
+// every other waiter of the same forward bails out as soon as it sees the word set, so the kernel terminates (with wrong
+// results). The host side surfaces it: Engine::run() ends every forward with launch_collect_status(), which moves the
+// word of every translation unit into the handle's pinned status word and CLEARS it (so one event cannot poison later
+// launches); the next fmmt_*_forward / fmmt_check on the handle then fails with FMMT_ERR_CUDA.
 __device__ unsigned int g_mbar_timeout = 0;
+// Each translation unit that includes this header has its own copy of the word (no relocatable device code); this
+// defines a host accessor for the copy of the including .cu file.
+#define FMMT_DEFINE_WATCHDOG_ADDR(fn)                           \
+  unsigned int* fn() {                                          \
+    void* p = nullptr;                                          \
+    if (cudaGetSymbolAddress(&p, g_mbar_timeout) != cudaSuccess) return nullptr; \
+    return static_cast<unsigned int*>(p);                       \
+  }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, uint32_t tag = 0) {
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {

@@ -27,7 +27,14 @@ def gather_valid_frames(faces: torch.Tensor, num_imgs: Sequence[int]) -> torch.T
 def evaluate_batch(swin_model, multimodal_model, batch, threshold: float = 0.2, gumbel: Optional[torch.Tensor] = None,
                    per_utterance: bool = True, return_intermediates: bool = False):
     """One iteration of multimodal_evaluate (train.py:164-234) -> (U, labels) logits on the GPU. Nothing here
-    synchronises the device: Swin -> filter/pack -> fusion are stream-ordered kernels."""
+    synchronises the device: Swin -> filter/pack -> fusion are stream-ordered kernels (call `.check()` on the two
+    modules, or use multimodal_evaluate, before trusting the logits).
+
+    Batch semantics at U > 1: `per_utterance=True` (default) gives every utterance the result the reference computes for
+    it at its default `trg_batch_size=1` (main.py:56) -- the only mode its published W-F1 was produced in. The reference's
+    literal batch code differs from that for U > 1 in two ways: the "no frame passes" fallback is decided for the whole
+    batch (train.py:187,223), and its re-pack loop has the `margin += n-1` off-by-one (train.py:200,213).
+    `per_utterance=False` reproduces the first (whole-batch fallback decision) but NOT the off-by-one."""
     (ids, mask, sep, audio, audio_mask, vision, vision_mask, _labels, faces, num_imgs, idx) = batch
     n = [int(x) for x in (num_imgs.tolist() if torch.is_tensor(num_imgs) else num_imgs)]
     frames = gather_valid_frames(faces.to("cuda", non_blocking=True), n)
@@ -54,6 +61,9 @@ def multimodal_evaluate(swin_model, multimodal_model, loader: Iterable, criterio
         results.append(logits)
         truths.append(labels)
         count += logits.shape[0]
+    for m in (swin_model, multimodal_model):       # surface a kernel pipeline-watchdog event before the logits are used
+        if hasattr(m, "check"):
+            m.check()
     return total_loss / max(count, 1), torch.cat(results), torch.cat(truths)
 
 
@@ -67,6 +77,8 @@ def unimodal_evaluate(unimodal_model, loader: Iterable, criterion=None):
         results.append(logits)
         truths.append(labels)
         count += logits.shape[0]
+    if hasattr(unimodal_model, "check"):
+        unimodal_model.check()
     return total_loss / max(count, 1), torch.cat(results), torch.cat(truths)
 
 

@@ -127,6 +127,11 @@ class _Module:
         self._finalized = True
         return self
 
+    def check(self):
+        """Synchronise this module's last forward and raise FmmtError if a kernel pipeline watchdog fired in any forward
+        since the previous check (include/facialmmt_b200.h fmmt_check). Call before trusting logits."""
+        _lib.check(self._lib.fmmt_check(self._h), "fmmt_check")
+
     # -- diagnostics
     def capture(self, name: str, numel: int) -> torch.Tensor:
         """Ask the next forward to copy a named fp32 intermediate into a new device tensor (parity tests)."""

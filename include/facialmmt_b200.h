@@ -113,6 +113,14 @@ FMMT_API int fmmt_multimodal_forward(fmmt_handle* h, const int64_t* ids, const i
 FMMT_API int fmmt_unimodal_forward(fmmt_handle* h, const float* inputs, const float* utt_mask, int U, float* logits,
                                    void* stream);
 
+/* Error surfacing for the asynchronous forwards (the reference raises Python exceptions synchronously). Every kernel
+ * pipeline wait is bounded by a watchdog; a timed-out wait terminates the kernel with invalid results instead of hanging
+ * the GPU. fmmt_check synchronises the stream of the handle's last forward and returns FMMT_ERR_CUDA if the watchdog fired
+ * in any forward since the previous check (fmmt_last_error names barrier / CTA / thread), else FMMT_OK. The next
+ * fmmt_*_forward on the handle reports the same condition if fmmt_check was not called. Callers check before they use
+ * logits (evaluate.py, bench.py and smoke() do). */
+FMMT_API int fmmt_check(fmmt_handle* h);
+
 /* Stage-wise parity hook: during the next forwards, copy the named fp32 intermediate into `dst` (device, `count`
  * floats). name == NULL clears all captures. Names: swin.patch_embed, swin.layer<l>.block<b>, swin.feat,
  * mm.text768, mm.text, mm.audio, mm.vision, mm.ta, mm.fused. */
@@ -122,9 +130,9 @@ FMMT_API int fmmt_set_capture(fmmt_handle* h, const char* name, float* dst, int6
  * profiling was enabled; returns the number of bytes needed (including the terminating NUL). */
 FMMT_API int fmmt_set_profile(fmmt_handle* h, int enable);
 FMMT_API int64_t fmmt_profile_read(fmmt_handle* h, char* buf, int64_t buf_len);
-/* Pipeline watchdog: non-zero if an mbarrier wait inside a GEMM kernel timed out since the last reset (a protocol bug;
- * the kernel then terminates with wrong results instead of hanging). Bit 31 set, bits 24-30 barrier id, 12-23 CTA,
- * 0-11 thread. Synchronises the device. */
+/* Pipeline watchdog word for the operator-level entry points (fmmt_op_*), which have no handle: non-zero if an mbarrier
+ * wait inside a kernel timed out since the last reset. Bit 31 set, bits 24-30 barrier id, 12-23 CTA, 0-11 thread.
+ * Synchronises the device. Model-level forwards report through fmmt_check instead. */
 FMMT_API uint32_t fmmt_debug_timeout(int reset);
 /* Bench probe: cycles per tcgen05.mma (M=128, N=n, K=16, bf16) issued back to back on resident shared-memory tiles, all
  * SMs at once (the tensor-pipe floor the GEMM roofline fractions are read against). Bits 16.. of n select a variant:
@@ -181,6 +189,12 @@ FMMT_API int fmmt_op_swin_mlp_stream(float* x, int M, int C, const float* gamma,
  * q rows (b*Lq+i), k/v rows (b*Lk+j), head h at columns [64h, 64h+64). key_mask fp32 (B,Lk) of 0/1 or NULL. */
 FMMT_API int fmmt_op_mha(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv, void* out, int ldo,
                          const float* key_mask, float mask_neg, int B, int H, int Lq, int Lk, float scale, void* stream);
+
+/* Target-utterance span extraction (src/models.py:112-150): text fp32 (U,L,H), sep_mask int64 (U,L), idx_in_dia int64 (U)
+ * -> out fp32 (U,max_len,H) zero-filled past the span, out_mask fp32 (U,max_len) of 0/1. text_kind FMMT_TEXT_ROBERTA: the
+ * span of utterance p > 0 starts 2 after the previous separator (<s> A </s></s> B </s>), FMMT_TEXT_BERT: 1 after. */
+FMMT_API int fmmt_op_span_extract(const float* text, const int64_t* sep_mask, const int64_t* idx_in_dia, int U, int L,
+                                  int H, int max_len, int text_kind, float* out, float* out_mask, void* stream);
 
 #ifdef __cplusplus
 }

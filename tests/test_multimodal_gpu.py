@@ -1,6 +1,6 @@
 """Fusion path (text encoder -> span -> audio/vision encoders -> cross-modal -> pooling -> logits) and the eval glue
-through the C ABI against the CPU oracle. bf16 operands / fp32 accumulate; north_star tolerance 1e-2 on logits,
-stated here relative to the logit scale of the stress-initialised model (max|logit| ~ 1.5)."""
+through the C ABI against the CPU oracle. bf16 operands / fp32 accumulate; north_star tolerance for this mode: 1e-2
+ABSOLUTE on the logits, argmax-exact (the fp32-grade mode is tested at 1e-3 in tests/test_precise_gpu.py)."""
 import pytest
 import torch
 
@@ -10,7 +10,7 @@ REL_TOL_STAGE = 4e-2
 
 
 def logit_tol(ref):
-    return 1e-2 * max(1.0, ref.abs().max().item())
+    return 1e-2          # absolute (north_star: "1e-2 bf16 on logits")
 
 
 def _mm(kind, layers):
