@@ -1,12 +1,18 @@
 #!/usr/bin/env python
 """Headline benchmark: utterances/s of the FacialMMT T+A+V eval forward (Swin-tiny over 160-frame face stacks ->
-frame filter -> RoBERTa-large text encoder -> audio/vision encoders -> CrossmodalTransformer fusion -> 7-way logits).
+frame filter -> RoBERTa/BERT-large text encoder -> audio/vision encoders -> CrossmodalTransformer fusion -> 7-way logits).
 
-  python bench.py --gpus N --steps K --warmup W          # this repo's CUDA path (one process per GPU under torchrun)
-  python bench.py --impl reference --gpus N ...           # the reference algorithm on the host cores (oracle port)
+  python bench.py --gpus N --steps K --warmup W           # this repo's CUDA path (one process per GPU under torchrun)
+  python bench.py --impl reference --gpus N ...            # the reference's own CPU implementation on the host cores
 
-One "step" = one eval batch of U=8 utterances per GPU (BASELINE.json configs[1]); weak scaling across GPUs
-(utterances are independent; the only exchange is an NCCL all-gather of the (U,7) logits). Prints ONE JSON line.
+Workloads (--workload; BASELINE.json configs):
+  tav_roberta_u8   configs[1]  T+A+V RoBERTa-large, U=8 utterances/GPU/step, L=128        (default, the headline metric)
+  tav_bert_u32     configs[2]  T+A+V BERT-large, U=32, bf16
+  tav_roberta_u32  configs[3]  RoBERTa-large, U=32 per GPU (= batch 256 sharded over 8 GPUs; run with --gpus 1/2/4/8)
+  tav_roberta_u1   latency of the reference's default trg_batch_size=1 (main.py:56)
+  swin160          configs[4]  Swin-tiny encoder isolation: one 160x3x224x224 face stack per step
+One "step" = one eval batch of U utterances per GPU; weak scaling across GPUs (utterances are independent; the only
+exchange is an NCCL all-gather of the (U,7) logits). Prints ONE JSON line.
 """
 from __future__ import annotations
 
@@ -25,20 +31,30 @@ FLOP_PER_FRAME = 9.018e9            # Swin-cls, 2*MAC
 FLOP_TEXT_L128 = 79.1e9
 FLOP_FUSION = 33.35e9
 
+WORKLOADS = {
+    "tav_roberta_u8": dict(plm="roberta-large", batch=8, baseline_config=1),
+    "tav_bert_u32": dict(plm="bert-large", batch=32, baseline_config=2),
+    "tav_roberta_u32": dict(plm="roberta-large", batch=32, baseline_config=3),
+    "tav_roberta_u1": dict(plm="roberta-large", batch=1, baseline_config=None),
+    "swin160": dict(plm=None, batch=1, baseline_config=4),
+}
 
-def ncu_traffic():
-    """DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture (profiles/): mean of
-    dram__bytes_read.sum + dram__bytes_write.sum over the captured launches of gemm_bf16_tcgen05_tma_kernel."""
-    p = os.path.join(ROOT, "profiles", "r01_ncu_full_swin160_top_kernels.json")
-    try:
-        rows = [r for r in json.load(open(p)) if r["kernel"].startswith("gemm_bf16_tcgen05_tma_kernel")]
-        if not rows:
-            return None, None
-        b = sum((r["dram_rd_MB"] + r["dram_wr_MB"]) * 1e6 for r in rows) / len(rows)
-        return b, (f"mean over {len(rows)} captured launches (Swin stages 1-2 of one 160-frame pass, cold L2: ncu flushes "
-                   f"caches between kernels), profiles/{os.path.basename(p)}")
-    except Exception:
-        return None, None
+
+def ncu_traffic(kernel_prefix="gemm_bf16_tcgen05_tma_kernel"):
+    """DRAM bytes per launch of the dominant kernel class from the committed `ncu --set full` capture of THIS build's
+    launch geometry (profiles/r02_ncu_top_kernels.json; falls back to the round-1 capture)."""
+    for name in ("r02_ncu_top_kernels.json", "r01_ncu_full_swin160_top_kernels.json"):
+        p = os.path.join(ROOT, "profiles", name)
+        try:
+            rows = [r for r in json.load(open(p)) if r["kernel"].startswith(kernel_prefix)]
+            if not rows:
+                continue
+            b = sum((r["dram_rd_MB"] + r["dram_wr_MB"]) * 1e6 for r in rows) / len(rows)
+            return b, (f"mean dram__bytes_read+write over {len(rows)} captured launches of {kernel_prefix} (ncu --set full, "
+                       f"cold L2: ncu flushes caches between kernels), profiles/{name}")
+        except Exception:
+            continue
+    return None, None
 
 
 def peaks():
@@ -101,91 +117,96 @@ class ClockSampler:
         return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def build_cfg(text_layers: int = 24):
+def build_cfg(plm="roberta-large", text_layers: int = 24):
     from facialmmt_b200.config import FmmtConfig, TextConfig
-    return FmmtConfig(text=TextConfig.roberta_large(text_layers))
+    t = TextConfig.bert_large(text_layers) if plm == "bert-large" else TextConfig.roberta_large(text_layers)
+    return FmmtConfig(text=t)
 
 
-def make_inputs(cfg, U, L, seed, device_faces=True):
-    """MELD-shaped synthetic batch; the 8x160 face stack is drawn on the GPU (uniform [-1,1], the value range of
-    ToTensor+Normalize(.5,.5)) because bicubic-upsampling 1280 crops on the host would dominate start-up."""
+def make_inputs(cfg, U, L, seed, ingest="f32"):
+    """MELD-shaped synthetic batch; the face stacks are drawn on the GPU because preparing U*160 crops on the host would
+    dominate start-up. ingest="f32": (U,160,3,224,224) fp32 uniform [-1,1] (the value range of ToTensor+Normalize(.5,.5),
+    utils/dataset.py:41-44); ingest="u8": (U,160,112,112,3) uint8 crops, resized + normalised on the device
+    (utils/dataset.py:47-69) inside the Swin forward."""
     import torch
     from facialmmt_b200 import synthetic as syn
     b = syn.synthetic_batch(cfg, U=U, L=L, seed=seed, with_faces=False)
     g = torch.Generator(device="cuda").manual_seed(seed)
     s = cfg.swin
-    b["faces"] = torch.rand(U, cfg.fusion.vision_len, 3, s.img_size, s.img_size, device="cuda", generator=g) * 2 - 1
+    if ingest == "u8":
+        b["faces"] = torch.randint(0, 256, (U, cfg.fusion.vision_len, 112, 112, 3), device="cuda", generator=g,
+                                   dtype=torch.uint8)
+    else:
+        b["faces"] = torch.rand(U, cfg.fusion.vision_len, 3, s.img_size, s.img_size, device="cuda", generator=g) * 2 - 1
     return b
 
 
-def cpu_reference_throughput(cfg, L, frames_sample=16, threads=None, swin_sd=None, mm_sd=None, repeats=1):
-    """utterances/s of the reference algorithm on the host cores (oracle port = torch-CPU fp32 restatement of the
-    reference modules). Bounded sample: Swin over `frames_sample` frames (scaled to 160) + one full fusion forward."""
-    import torch
-    from facialmmt_b200 import synthetic as syn
-    from oracle import facialmmt_oracle as orc
-    if threads:
-        torch.set_num_threads(threads)
-    swin_sd = swin_sd or syn.swin_cls_stress_state_dict(cfg.swin, 1111)
-    mm_sd = mm_sd or syn.multimodal_stress_state_dict(cfg, 1111)
-    b = syn.synthetic_batch(cfg, U=1, L=L, seed=5, with_faces=False)
-    frames = syn.synthetic_faces(frames_sample, 3)
-    g = -torch.empty(frames_sample, 7).exponential_().log()
-    best = None
-    with torch.no_grad():
-        for _ in range(repeats + 1):     # first pass = warm-up
-            t0 = time.perf_counter()
-            z = orc.swin_cls_logits(swin_sd, frames)
-            probs = orc.gumbel_softmax_probs(z, g, 1.0)
-            t1 = time.perf_counter()
-            p160 = probs.repeat(160 // frames_sample + 1, 1)[:160]
-            v519, nm = orc.filter_pack(b["vision"], b["vision_mask"], [160], p160, cfg.threshold)
-            orc.multimodal_forward(mm_sd, b["text_ids"], b["text_mask"], b["sep_mask"], b["audio"], b["audio_mask"], v519,
-                                   nm, b["idx_in_dia"], kind=cfg.text.kind)
-            t2 = time.perf_counter()
-            t_utt = (t1 - t0) * (160.0 / frames_sample) + (t2 - t1)
-            best = t_utt if best is None else min(best, t_utt)
-    return 1.0 / best, torch.get_num_threads(), (f"Swin-cls over {frames_sample} frames scaled x{160 // frames_sample} "
-                                                  f"+ one full T+A+V fusion forward (U=1, L={L}), fp32, best of {repeats}")
+def workload_config(args, world):
+    w = WORKLOADS[args.workload]
+    if args.workload == "swin160":
+        return {"workload": f"swin160: Swin-tiny facial encoder isolation (BASELINE configs[4]), {args.batch} x 160x3x224x224 "
+                            f"face stack(s) per GPU per step -> 160x7 aux distributions + 160x512 features, synthetic",
+                "global_batch": args.batch * world, "frames_per_utterance": 160, "precision": args.precision,
+                "parallelism": f"replicas x{world}", "l2": "96 MB of faces per stack + ~1 GB of activations per step exceed the 126 MB L2; no explicit flush"}
+    return {"workload": f"{args.workload}: T+A+V {w['plm']} --doEval forward (BASELINE configs[{w['baseline_config']}]), "
+                        f"U={args.batch} utterances/GPU/step, 160 face frames per utterance "
+                        f"({'112x112x3 uint8 crops resized on device' if args.ingest == 'u8' else '3x224x224 fp32'}, synthetic), "
+                        f"{args.text_len}-token dialogue text, 160x768 audio, 160x512 vision",
+            "global_batch": args.batch * world, "text_len": args.text_len, "frames_per_utterance": 160,
+            "precision": args.precision, "ingest": args.ingest,
+            "batch_semantics": "per-utterance filter fallback (== the reference at its default trg_batch_size=1; its U>1 "
+                               "re-pack off-by-one, train.py:200,213, is not reproduced)",
+            "parallelism": f"utterance sharding x{world} (NCCL all-gather of logits)",
+            "l2": "inputs + activations per step (>= 0.8 GB) exceed the 126 MB L2; no explicit flush"}
+
+
+def flop_per_utt(args):
+    if args.workload == "swin160":
+        return 160 * FLOP_PER_FRAME
+    return 160 * FLOP_PER_FRAME + FLOP_TEXT_L128 * args.text_len / 128 + FLOP_FUSION
 
 
 def run_reference(args):
-    """--impl reference: the reference's CPU implementation of the path (oracle port), rank 0 only."""
+    """--impl reference: the reference's OWN CPU implementation (unmodified modules + train.py eval loop from
+    baseline/_ref or /root/reference; oracle port only if neither exists), rank 0 only, all host threads. Each step is one
+    FULL eval batch of --ref-batch utterances (default 1 = the reference's trg_batch_size default): a bounded sample of the
+    GPU arm's step; ms_per_step is measured, nothing is extrapolated."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     import torch
-    from facialmmt_b200 import synthetic as syn
-    # torchrun exports OMP_NUM_THREADS=1; the reference arm is meant to use every host core
-    torch.set_num_threads(max(1, os.cpu_count() or 1))
-    cfg = build_cfg()
-    swin_sd = syn.swin_cls_stress_state_dict(cfg.swin, 1111)
-    mm_sd = syn.multimodal_stress_state_dict(cfg, 1111)
-    vals = []
-    for i in range(args.warmup + args.steps):
-        v, cores, sample = cpu_reference_throughput(cfg, args.text_len, frames_sample=8, swin_sd=swin_sd, mm_sd=mm_sd,
-                                                    repeats=1)
-        if i >= args.warmup:
-            vals.append(v)
-    value = len(vals) / sum(1.0 / v for v in vals)
+    from oracle.ref_bench import ReferenceRunner, summarize
+    w = WORKLOADS[args.workload]
+    cfg = build_cfg(w["plm"] or "roberta-large")
+    runner = ReferenceRunner(cfg, args.text_len, plm=w["plm"] or "roberta-large")   # sets all host threads
+    U = args.ref_batch
+    b = runner.batch(U, 1111)
+    times = []
+    if args.workload == "swin160":
+        frames = b["faces"].reshape(-1, 3, 224, 224)
+        for i in range(args.warmup + args.steps):
+            t0 = time.perf_counter()
+            runner.swin_logits(frames)
+            dt = time.perf_counter() - t0
+            if i >= args.warmup:
+                times.append(dict(total=dt, swin=dt, glue=0.0, fusion=0.0))
+    else:
+        for i in range(args.warmup + args.steps):
+            t = runner.step(b)
+            if i >= args.warmup:
+                times.append(t)
+    cb = summarize(runner, times, U)
+    value = cb["value"]
     out = {
         "impl": "reference", "metric": "utterances/sec (160-frame T+A+V fusion fwd)", "value": value,
         "unit": "utterances/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": 1000.0 * args.batch / value, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f32", "data": "synthetic",
-        "config": workload_config(args, 1),
-        "cpu_baseline": {"value": value, "unit": "utterances/s", "cores": cores, "kind": "port", "sample": sample},
+        "ms_per_step": 1000.0 * sum(t["total"] for t in times) / len(times), "utterances_per_step": U,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic", "config": workload_config(args, 1),
+        "cpu_baseline": cb,
         "e2e": {"value": value, "unit": "utterances/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(out), flush=True)
-
-
-def workload_config(args, world):
-    return {"workload": f"T+A+V RoBERTa-large --doEval forward, U={args.batch} utterances/GPU, 160x3x224x224 face stack "
-                        f"per utterance (synthetic), {args.text_len}-token dialogue text, 160x768 audio, 160x512 vision",
-            "global_batch": args.batch * world, "text_len": args.text_len, "frames_per_utterance": 160,
-            "parallelism": f"utterance sharding x{world} (NCCL all-gather of logits)",
-            "l2": "inputs (770 MB of faces per step) exceed the 126 MB L2; no explicit flush"}
 
 
 def run_ours(args):
@@ -204,47 +225,56 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     lib = _lib.load()
-    cfg = build_cfg()
+    w = WORKLOADS[args.workload]
+    swin_only = args.workload == "swin160"
+    cfg = build_cfg(w["plm"] or "roberta-large")
     U, L = args.batch, args.text_len
-    swin = SwinForAffwildClassification(cfg, swin_chunk=args.swin_chunk, swin_chunk_late=args.swin_chunk_late)
+    swin = SwinForAffwildClassification(cfg, swin_chunk=args.swin_chunk, swin_chunk_late=args.swin_chunk_late,
+                                        precision=args.precision)
     swin_sd = syn.swin_cls_stress_state_dict(cfg.swin, 1111)
-    mm_sd = syn.multimodal_stress_state_dict(cfg, 1111)
     swin.load_state_dict(swin_sd)
-    mm = MultiModalTransformerForClassification(cfg)
-    mm.load_state_dict(mm_sd)
-    if not (rank == 0 and world == 1 and not args.no_cpu_baseline):
-        del swin_sd, mm_sd
+    mm = None
+    if not swin_only:
+        mm = MultiModalTransformerForClassification(cfg, precision=args.precision)
+        mm_sd = syn.multimodal_stress_state_dict(cfg, 1111)
+        mm.load_state_dict(mm_sd)
+        del mm_sd
+    mods = [m for m in (swin, mm) if m is not None]
 
-    b = make_inputs(cfg, U, L, seed=1111 + 1000 * rank)
+    b = make_inputs(cfg, U, L, seed=1111 + 1000 * rank, ingest=args.ingest)
     dev = {k: (v.cuda() if torch.is_tensor(v) else v) for k, v in b.items()}
     n_imgs = [int(x) for x in b["num_imgs"]]
     labels = torch.zeros(U, dtype=torch.long)
-    gathered = torch.empty(world * U, cfg.fusion.num_labels, device="cuda") if world > 1 else None
+    n_out = cfg.fusion.num_labels
+    gathered = torch.empty(world * U, n_out, device="cuda") if world > 1 else None
 
-    def step_local():
-        batch = (dev["text_ids"], dev["text_mask"], dev["sep_mask"], dev["audio"], dev["audio_mask"], dev["vision"],
-                 dev["vision_mask"], labels, dev["faces"], n_imgs, dev["idx_in_dia"])
-        return evaluate_batch(swin, mm, batch, cfg.threshold, gumbel=dev["gumbel"])
+    def forward(d):
+        if swin_only:
+            frames = d["faces"].reshape(U * cfg.fusion.vision_len, *d["faces"].shape[2:])
+            return swin.forward_full(frames, d["gumbel"])[1]            # (U*160, 7) aux distributions
+        batch = (d["text_ids"], d["text_mask"], d["sep_mask"], d["audio"], d["audio_mask"], d["vision"],
+                 d["vision_mask"], labels, d["faces"], n_imgs, d["idx_in_dia"])
+        return evaluate_batch(swin, mm, batch, cfg.threshold, gumbel=d["gumbel"])
 
     def step_device():
-        logits = step_local()
-        if world > 1:
-            dist.all_gather_into_tensor(gathered, logits)
+        out = forward(dev)
+        if world > 1 and not swin_only:
+            dist.all_gather_into_tensor(gathered, out)
             return gathered
-        return logits
+        return out
 
     # ---- host-resident copy of the inputs for the end-to-end leg (pinned)
     host = {k: v.cpu().pin_memory() for k, v in dev.items() if torch.is_tensor(v)}
     h2d_bytes = sum(v.numel() * v.element_size() for k, v in host.items() if k != "num_imgs")
-    out_host = torch.empty(world * U, cfg.fusion.num_labels).pin_memory()
+    out_shape = (U * cfg.fusion.vision_len, n_out) if swin_only else (world * U, n_out)
     # End-to-end leg: inputs start in pinned HOST memory every step. The H2D copy of step i+1 runs on a copy stream
-    # while step i computes (two device-side input sets), and the logits of step i are read back to the host inside the
+    # while step i computes (two device-side input sets), and the result of step i is read back to the host inside the
     # timed region; the caller holds every result on the host when the clock stops.
     copy_stream = torch.cuda.Stream()
     dev_sets = [None, None]
     ready = [torch.cuda.Event(), torch.cuda.Event()]
     consumed = [torch.cuda.Event(), torch.cuda.Event()]
-    out_hosts = [torch.empty(world * U, cfg.fusion.num_labels).pin_memory() for _ in range(2)]
+    out_hosts = [torch.empty(*out_shape).pin_memory() for _ in range(2)]
     state = {"i": 0}
 
     def stage_inputs(slot):
@@ -264,14 +294,11 @@ def run_ours(args):
         stage_inputs(slot ^ 1)                              # prefetch the next step's inputs behind this step's compute
         cur = torch.cuda.current_stream()
         cur.wait_event(ready[slot])
-        d = dev_sets[slot]
-        batch = (d["text_ids"], d["text_mask"], d["sep_mask"], d["audio"], d["audio_mask"], d["vision"],
-                 d["vision_mask"], labels, d["faces"], n_imgs, d["idx_in_dia"])
-        logits = evaluate_batch(swin, mm, batch, cfg.threshold, gumbel=d["gumbel"])
-        if world > 1:
-            dist.all_gather_into_tensor(gathered, logits)
-            logits = gathered
-        out_hosts[slot].copy_(logits, non_blocking=True)
+        out = forward(dev_sets[slot])
+        if world > 1 and not swin_only:
+            dist.all_gather_into_tensor(gathered, out)
+            out = gathered
+        out_hosts[slot].copy_(out, non_blocking=True)
         consumed[slot].record(cur)
         state["i"] = i + 1
         return out_hosts[slot]
@@ -294,6 +321,8 @@ def run_ours(args):
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
+        for m in mods:
+            m.check()                                       # a pipeline-watchdog event invalidates the number
         ms = torch.tensor([e0.elapsed_time(e1)], device="cuda")
         if world > 1:
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
@@ -309,32 +338,96 @@ def run_ours(args):
     if not args.no_e2e:
         e2e_ms, _ = timed(step_e2e, e2e_steps, 1)
 
+    # ---- parity of THIS configuration (outside the timed regions, rank 0, N=1): frames-per-pass invariance bit for bit
+    parity = None
+    ref_runner = None
+    if rank == 0 and world == 1 and not args.no_parity:
+        parity = {}
+        frames0 = dev["faces"][0]                                        # first utterance's 160 frames
+        g0 = dev["gumbel"][:frames0.shape[0]]
+        big = swin.forward_full(dev["faces"].reshape(U * cfg.fusion.vision_len, *dev["faces"].shape[2:]), dev["gumbel"])
+        small = SwinForAffwildClassification(cfg, swin_chunk=7, swin_chunk_late=13, precision=args.precision)
+        small.load_state_dict(swin_sd)
+        sm = small.forward_full(frames0, g0)
+        small.check(); swin.check()
+        nf0 = frames0.shape[0]
+        parity["frames_per_pass_invariance"] = bool(torch.equal(big[0][:nf0], sm[0]) and torch.equal(big[1][:nf0], sm[1]))
+        parity["frames_per_pass_invariance_note"] = (f"Swin logits/probs of utterance 0 inside the {U * 160}-frame default "
+                                                     f"passes == the same 160 frames through passes of 7/13 frames, bit for bit")
+        del small
+        if not args.no_cpu_baseline:
+            # the reference's own Swin-cls on the first 16 frames of the benchmarked input vs the device logits
+            from oracle.ref_bench import ReferenceRunner
+            ref_runner = ReferenceRunner(cfg, L, plm=w["plm"] or "roberta-large")
+            if args.ingest == "u8":
+                from oracle import frame_ingest as fi
+                f16 = torch.stack([fi.ingest_frame(x.cpu().numpy()) for x in frames0[:16]])
+            else:
+                f16 = frames0[:16].cpu()
+            ref_logits = ref_runner.swin_logits(f16)
+            err = (big[0][:16].cpu() - ref_logits).abs().max().item()
+            parity["swin_logits_max_abs_err_vs_" + ref_runner.kind] = err
+            parity["swin_logits_frames"] = 16
+            parity["swin_logits_tol"] = 2e-2 if args.precision == "bf16" else 1e-3
+            parity["ok"] = bool(parity["frames_per_pass_invariance"] and err < parity["swin_logits_tol"])
+        else:
+            parity["ok"] = bool(parity["frames_per_pass_invariance"])
+
+    # ---- U=1 latency (the reference's default trg_batch_size=1): device-timed, inputs resident
+    lat = None
+    if rank == 0 and world == 1 and not swin_only and not args.no_latency:
+        d1 = {k: (v[:1].contiguous() if torch.is_tensor(v) and v.shape[0] == U else v) for k, v in dev.items()}
+        d1["gumbel"] = dev["gumbel"][:cfg.fusion.vision_len].contiguous()
+        n1 = n_imgs[:1]
+        lab1 = labels[:1]
+
+        def step_u1():
+            batch = (d1["text_ids"], d1["text_mask"], d1["sep_mask"], d1["audio"], d1["audio_mask"], d1["vision"],
+                     d1["vision_mask"], lab1, d1["faces"], n1, d1["idx_in_dia"])
+            return evaluate_batch(swin, mm, batch, cfg.threshold, gumbel=d1["gumbel"])
+        for _ in range(3):
+            step_u1()
+        torch.cuda.synchronize()
+        ts = []
+        for _ in range(10):
+            t0 = time.perf_counter()
+            step_u1().cpu()                     # wall clock from the call to the logits on the host
+            ts.append((time.perf_counter() - t0) * 1e3)
+        lat = {"batch": 1, "ms_median_wall": statistics.median(ts), "ms_min_wall": min(ts),
+               "note": "U=1 eval batch (160 frames), wall clock from the call to logits on the host, inputs resident in HBM"}
+
     # ---- per-kernel event profile of one extra step (same stream) for the roofline object
     roof = None
     if rank == 0 and not args.no_e2e:
-        swin.set_profile(True)
-        mm.set_profile(True)
-        step_local()                      # rank-local: no collective here (the other ranks are not in this step)
+        for m in mods:
+            m.set_profile(True)
+        forward(dev)                      # rank-local: no collective here (the other ranks are not in this step)
         torch.cuda.synchronize()
         prof = {}
-        for k, v in list(swin.read_profile().items()) + list(mm.read_profile().items()):
-            a = prof.setdefault(k, {"ms": 0.0, "flops": 0.0, "bytes": 0.0, "launches": 0})
-            for f in a:
-                a[f] += v[f]
-        swin.set_profile(False)
-        mm.set_profile(False)
+        for m in mods:
+            for k, v in m.read_profile().items():
+                a = prof.setdefault(k, {"ms": 0.0, "flops": 0.0, "bytes": 0.0, "launches": 0})
+                for f in a:
+                    a[f] += v[f]
+            m.set_profile(False)
         pk = peaks()
-        # every tcgen05 GEMM-class launch: the Linear-layer GEMMs and the fused MLP kernels (LN + fc1 + GELU + fc2 + residual)
-        gem = [v for k, v in prof.items() if k.startswith("gemm ") or k.startswith("mlp_fused")]
+        # every tcgen05 GEMM-class launch: Linear-layer GEMMs, fused MLP kernels, fused attention half-blocks
+        gem = [v for k, v in prof.items() if k.startswith(("gemm ", "mlp_fused", "attn_fused"))]
         g_ms = sum(v["ms"] for v in gem); g_fl = sum(v["flops"] for v in gem); g_n = sum(v["launches"] for v in gem)
         all_ms = sum(v["ms"] for v in prof.values())
         achieved = g_fl / (g_ms * 1e-3) / 1e12 if g_ms > 0 else 0.0
-        roof = {"bound": "tensor", "kernel": "gemm_bf16_tcgen05_tma_kernel + fused MLP kernels (every Linear layer of the step)",
+        traffic, traffic_src = ncu_traffic()
+        roof = {"bound": "tensor", "kernel": "tcgen05 GEMM-class launches of the step (gemm_bf16_tcgen05_tma_kernel, fused MLP "
+                                             "and fused attention half-block kernels: every Linear layer of the path)",
                 "achieved": achieved, "peak": pk["tf_sustained"], "unit": "TFLOP/s",
-                "frac": achieved / pk["tf_sustained"], "traffic": ncu_traffic()[0], "traffic_source": ncu_traffic()[1],
-                "peak_source": pk["source"] + ", sustained bf16 figure (kernel timed inside a long step)",
+                "frac": achieved / pk["tf_sustained"], "traffic": traffic, "traffic_source": traffic_src,
+                "peak_source": pk["source"] + ", sustained bf16 figure (kernels timed inside a long step)",
                 "launches_per_step": g_n, "flops_per_launch": g_fl / max(g_n, 1), "avg_launch_ms": g_ms / max(g_n, 1),
                 "share_of_step_kernel_time": g_ms / all_ms if all_ms > 0 else None}
+        top = sorted(prof.items(), key=lambda kv: -kv[1]["ms"])[:6]
+        roof["top_kernels"] = [{"kernel": k, "ms": round(v["ms"], 4), "launches": v["launches"],
+                                "tflops": round(v["flops"] / max(v["ms"], 1e-9) / 1e9, 1),
+                                "gbs": round(v["bytes"] / max(v["ms"], 1e-9) / 1e6, 1)} for k, v in top]
         if args.profile_out:
             json.dump(prof, open(args.profile_out, "w"), indent=1, sort_keys=True)
 
@@ -343,23 +436,42 @@ def run_ours(args):
     e2e_value = world * U * e2e_steps / (e2e_ms * 1e-3)
     if rank == 0:
         pk = peaks()
-        flop_per_utt = 160 * FLOP_PER_FRAME + (FLOP_TEXT_L128 if L == 128 else FLOP_TEXT_L128 * L / 128) + FLOP_FUSION
         out = {
-            "metric": "utterances/sec (160-frame T+A+V fusion fwd)", "value": value, "unit": "utterances/s",
+            "metric": "utterances/sec (160-frame T+A+V fusion fwd)" if not swin_only
+                      else "utterance face stacks/sec (160-frame Swin-tiny encoder fwd)",
+            "value": value, "unit": "utterances/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": workload_config(args, world),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16" if args.precision == "bf16" else "bf16x3 (fp32-grade split operands, fp32 accumulate)",
+            "data": "synthetic", "config": workload_config(args, world),
             "e2e": {"value": e2e_value, "unit": "utterances/s", "h2d_bytes_per_step": int(h2d_bytes),
-                    "d2h_bytes_per_step": int(out_host.numel() * 4), "steps": e2e_steps},
+                    "d2h_bytes_per_step": int(out_hosts[0].numel() * 4), "steps": e2e_steps},
             "gpu_launches": gpu_launches,
             "clocks": clocks,
             "roofline": roof,
-            "path_tensor_frac": value / world * flop_per_utt / (pk["tf_sustained"] * 1e12),
+            "path_tensor_frac": value / world * flop_per_utt(args) / (pk["tf_sustained"] * 1e12),
+            "parity_checked": bool(parity and parity.get("ok")), "parity": parity,
+            "latency_u1": lat,
         }
+        if swin_only:
+            out["frames_per_s"] = value * 160
         if world == 1 and not args.no_cpu_baseline:
-            torch.set_num_threads(max(1, os.cpu_count() or 1))
-            v, cores, sample = cpu_reference_throughput(cfg, L, frames_sample=8, swin_sd=swin_sd, mm_sd=mm_sd)
-            out["cpu_baseline"] = {"value": v, "unit": "utterances/s", "cores": cores, "kind": "port", "sample": sample}
+            from oracle.ref_bench import ReferenceRunner, summarize
+            if ref_runner is None:
+                ref_runner = ReferenceRunner(cfg, L, plm=w["plm"] or "roberta-large")
+            rb = ref_runner.batch(1, 1111)
+            times = []
+            for i in range(1 + args.cpu_baseline_batches):      # first = warm-up
+                if swin_only:
+                    t0 = time.perf_counter()
+                    ref_runner.swin_logits(rb["faces"].reshape(-1, 3, 224, 224))
+                    dt = time.perf_counter() - t0
+                    t = dict(total=dt, swin=dt, glue=0.0, fusion=0.0)
+                else:
+                    t = ref_runner.step(rb)
+                if i > 0:
+                    times.append(t)
+            out["cpu_baseline"] = summarize(ref_runner, times, 1)
         print(json.dumps(out), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -371,14 +483,26 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=8, help="utterances per GPU per step (BASELINE.json configs[1]: 8)")
+    ap.add_argument("--workload", default="tav_roberta_u8", choices=sorted(WORKLOADS))
+    ap.add_argument("--batch", type=int, default=0, help="utterances per GPU per step (0 = the workload's own)")
     ap.add_argument("--text-len", type=int, default=128)
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"],
+                    help="bf16: bf16 operands / fp32 accumulate (1e-2 bar); fp32: split-bf16 x3 operands (1e-3 bar)")
+    ap.add_argument("--ingest", default="f32", choices=["f32", "u8"],
+                    help="f32: (3,224,224) fp32 frames as the reference's DataLoader yields; u8: 112x112 uint8 crops, resized "
+                         "and normalised on the device (utils/dataset.py:47-69)")
+    ap.add_argument("--ref-batch", type=int, default=1, help="--impl reference: utterances per step (bounded sample)")
+    ap.add_argument("--cpu-baseline-batches", type=int, default=2)
     ap.add_argument("--swin-chunk", type=int, default=0)
     ap.add_argument("--swin-chunk-late", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-parity", action="store_true")
+    ap.add_argument("--no-latency", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer end-to-end leg (profiling runs)")
     ap.add_argument("--profile-out", default=None, help="write the per-kernel event profile of one step as JSON")
     args = ap.parse_args()
+    if args.batch <= 0:
+        args.batch = WORKLOADS[args.workload]["batch"]
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3
     if args.impl == "reference":

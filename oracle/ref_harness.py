@@ -1,8 +1,9 @@
-"""TEST INFRASTRUCTURE ONLY -- imports the *real* reference (NUSTM/FacialMMT) from /root/reference on CPU.
+"""TEST / BASELINE INFRASTRUCTURE ONLY -- imports the *real* reference (NUSTM/FacialMMT) on CPU.
 
-Used in the build container to (a) pin oracle/facialmmt_oracle.py against the reference's own modules and
-(b) generate the golden vectors under tests/golden/ (tests/golden/make_golden.py). /root/reference does not exist
-on the GPU box, so nothing that runs there may import this module. No reference source is copied.
+Used (a) in the build container to pin oracle/facialmmt_oracle.py against the reference's own modules and to generate
+the golden vectors under tests/golden/ (tests/golden/make_golden.py), from /root/reference; (b) by bench.py's CPU legs
+(`--impl reference`, `cpu_baseline`) on the GPU box, from the unmodified copy that oracle/make_ref.py places in the
+git-ignored baseline/_ref/ (/root/reference does not exist there). Never imported by the product package.
 
 Three shims make the reference importable on CPU with the installed library versions:
   1. `timm` is not installed: a stand-in module provides DropPath / to_2tuple / trunc_normal_
@@ -18,7 +19,20 @@ import os
 import sys
 import types
 
-REFERENCE_ROOT = os.environ.get("FMMT_REFERENCE_ROOT", "/root/reference")
+_REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _find_root() -> str:
+    env = os.environ.get("FMMT_REFERENCE_ROOT")
+    if env:
+        return env
+    for cand in ("/root/reference", os.path.join(_REPO, "baseline", "_ref")):
+        if os.path.isfile(os.path.join(cand, "src", "models.py")):
+            return cand
+    return "/root/reference"
+
+
+REFERENCE_ROOT = _find_root()
 
 
 def available() -> bool:
@@ -118,3 +132,22 @@ def build_unimodal(args=None):
     install_shims()
     from src.models import meld_utt_transformer
     return meld_utt_transformer(args or default_args()).eval()
+
+
+def literal_eval_loop():
+    """The reference's own `multimodal_evaluate` (train.py:154-243) as a callable factory, obtained by exec'ing its source
+    text at run time (train.py itself cannot be imported: it needs pytorch_lightning). Nothing is copied into the repo.
+    `make(args, loader)` -> multimodal_evaluate(shareSwin_model, multimodal_model, criterion, test)."""
+    import textwrap
+
+    import torch
+    lines = open(os.path.join(REFERENCE_ROOT, "train.py")).read().splitlines()
+    start = next(i for i, l in enumerate(lines) if l.strip().startswith("def multimodal_evaluate("))
+    end = next(i for i in range(start + 1, len(lines)) if lines[i].strip().startswith("def "))
+    src = textwrap.dedent("\n".join(lines[start:end]))
+
+    def make(args, loader):
+        ns = {"torch": torch, "args": args, "trg_test_loader": loader, "trg_valid_loader": loader}
+        exec(compile(src, "reference:train.py:multimodal_evaluate", "exec"), ns)
+        return ns["multimodal_evaluate"]
+    return make

@@ -22,7 +22,6 @@ from __future__ import annotations
 import argparse
 import os
 import sys
-import textwrap
 
 import numpy as np
 import torch
@@ -41,18 +40,7 @@ def checksum(sd) -> float:
     return float(sum(v.double().abs().sum() for v in sd.values() if v.is_floating_point()))
 
 
-def literal_eval_loop():
-    """Return the reference's own `multimodal_evaluate` as a callable, by exec'ing its source text from train.py."""
-    lines = open(os.path.join(rh.REFERENCE_ROOT, "train.py")).read().splitlines()
-    start = next(i for i, l in enumerate(lines) if l.strip().startswith("def multimodal_evaluate("))
-    end = next(i for i in range(start + 1, len(lines)) if lines[i].strip().startswith("def "))
-    src = textwrap.dedent("\n".join(lines[start:end]))
-
-    def make(args, loader):
-        ns = {"torch": torch, "args": args, "trg_test_loader": loader, "trg_valid_loader": loader}
-        exec(compile(src, "reference:train.py:multimodal_evaluate", "exec"), ns)
-        return ns["multimodal_evaluate"]
-    return make
+literal_eval_loop = rh.literal_eval_loop
 
 
 class _SwinStub(torch.nn.Module):

@@ -79,7 +79,10 @@ def test_bench_config_frames_per_pass_invariance_and_oracle(bench_models):
           f"aux logits err {lerr:.3e}, probs err {perr:.3e}")
     assert perr < PROB_TOL_ABS
     assert ferr < 2e-2 * max(1.0, ref_feat.abs().max().item())
-    assert torch.equal(logits[sel.cuda()].cpu().argmax(-1), ref_logits.argmax(-1))
+    top2 = ref_logits.topk(2, -1).values
+    clear = (top2[:, 0] - top2[:, 1]) > 2 * lerr              # near-ties of this INTERMEDIATE head are not decidable
+    assert clear.sum() >= len(idx) // 2
+    assert torch.equal(logits[sel.cuda()].cpu().argmax(-1)[clear], ref_logits.argmax(-1)[clear])
     # (iii) the whole eval batch: U=8, RoBERTa-large 24 L
     batch = (b["text_ids"], b["text_mask"], b["sep_mask"], b["audio"], b["audio_mask"], b["vision"], b["vision_mask"],
              torch.zeros(U, dtype=torch.long), b["faces"], b["num_imgs"], b["idx_in_dia"])
