@@ -14,6 +14,7 @@ LIB_PATH = Path(__file__).resolve().parent / "libfacialmmt_b200.so"
 
 MODEL_SWIN_CLS, MODEL_MULTIMODAL, MODEL_UNIMODAL = 1, 2, 3
 TEXT_ROBERTA, TEXT_BERT = 0, 1
+PRECISION_BF16, PRECISION_FP32 = 0, 1
 
 
 class FmmtError(RuntimeError):
@@ -36,6 +37,7 @@ class FmmtConfigC(Structure):
         ("cmt_layers_ta", c_int32), ("cmt_heads_ta", c_int32), ("cmt_layers_tav", c_int32), ("cmt_heads_tav", c_int32),
         ("text_len", c_int32), ("audio_len", c_int32), ("vision_len", c_int32),
         ("eps", c_float),
+        ("precision", c_int32),
     ]
 
 

@@ -406,9 +406,156 @@ __global__ void __launch_bounds__(128) mha_flash_kernel(const MhaParams p) {
   }
 }
 
+// ------------------------------------------------------------------------------------------ fp32-grade mode (SIMT)
+// Plain fp32 math for the 1e-3 parity mode (the bf16 tensor-core cores above are the speed build). One thread per query
+// row; K and V of the (window | key tile, head) staged in shared memory as fp32. Outputs are written as the split-bf16
+// operand [hi | lo | hi] of the following Linear (see kernels.cu store_split4).
+__device__ __forceinline__ void store_split1(__nv_bfloat16* row, int width, int col, float y) {
+  const __nv_bfloat16 hi = __float2bfloat16(y);
+  const __nv_bfloat16 lo = __float2bfloat16(y - __bfloat162float(hi));
+  row[col] = hi;
+  row[width + col] = lo;
+  row[2 * width + col] = hi;
+}
+
+__global__ void __launch_bounds__(64) window_attention_f32_kernel(const float* __restrict__ qkv, __nv_bfloat16* __restrict__ out,
+                                                                  const float* __restrict__ bias,
+                                                                  const int8_t* __restrict__ rid, int nW, int C, int N,
+                                                                  float scale) {
+  __shared__ float sK[49][WA_D + 1];
+  __shared__ float sV[49][WA_D + 1];
+  __shared__ int8_t sR[64];
+  const int w = blockIdx.x, h = blockIdx.y, t = threadIdx.x;
+  const size_t ld = static_cast<size_t>(3) * C;
+  const float* base = qkv + static_cast<size_t>(w) * N * ld + h * WA_D;
+  for (int idx = t; idx < N * WA_D; idx += 64) {
+    const int r = idx / WA_D, d = idx - r * WA_D;
+    sK[r][d] = base[r * ld + C + d];
+    sV[r][d] = base[r * ld + 2 * C + d];
+  }
+  if (t < N) sR[t] = rid != nullptr ? rid[(w % nW) * N + t] : 0;
+  __syncthreads();
+  if (t >= N) return;
+  float q[WA_D];
+#pragma unroll
+  for (int d = 0; d < WA_D; ++d) q[d] = base[t * ld + d] * scale;       // q * scale before QK^T (Swin_Transformer.py:123)
+  float sc[49];
+  float mx = -INFINITY;
+  const float* bh = bias + (static_cast<size_t>(h) * N + t) * N;
+  const int8_t myr = sR[t];
+  for (int j = 0; j < N; ++j) {
+    float a = 0.f;
+#pragma unroll
+    for (int d = 0; d < WA_D; ++d) a = fmaf(q[d], sK[j][d], a);
+    a += bh[j];
+    if (rid != nullptr && sR[j] != myr) a += -100.0f;
+    sc[j] = a;
+    mx = fmaxf(mx, a);
+  }
+  float sum = 0.f;
+  for (int j = 0; j < N; ++j) {
+    sc[j] = expf(sc[j] - mx);
+    sum += sc[j];
+  }
+  const float inv = 1.0f / sum;
+  float o[WA_D];
+#pragma unroll
+  for (int d = 0; d < WA_D; ++d) o[d] = 0.f;
+  for (int j = 0; j < N; ++j) {
+    const float pj = sc[j] * inv;
+#pragma unroll
+    for (int d = 0; d < WA_D; ++d) o[d] = fmaf(pj, sV[j][d], o[d]);
+  }
+  __nv_bfloat16* orow = out + (static_cast<size_t>(w) * N + t) * ld;     // split row: 3C wide
+#pragma unroll
+  for (int d = 0; d < WA_D; ++d) store_split1(orow, C, h * WA_D + d, o[d]);
+}
+
+constexpr int F32_BK = 32;
+__global__ void __launch_bounds__(64) mha_f32_kernel(const float* __restrict__ q, int ldq, const float* __restrict__ k, int ldk,
+                                                     const float* __restrict__ v, int ldv, __nv_bfloat16* __restrict__ out,
+                                                     int width, const float* __restrict__ key_mask, float mask_neg, int Lq,
+                                                     int Lk, float scale) {
+  __shared__ float sK[F32_BK][FA_D + 1];
+  __shared__ float sV[F32_BK][FA_D + 1];
+  __shared__ float sM[F32_BK];
+  const int q0 = blockIdx.x * 64, h = blockIdx.y, b = blockIdx.z, t = threadIdx.x;
+  const int qi = q0 + t;
+  const bool active = qi < Lq;
+  float qr[FA_D];
+#pragma unroll
+  for (int d = 0; d < FA_D; ++d) qr[d] = active ? q[(static_cast<size_t>(b) * Lq + qi) * ldq + h * FA_D + d] * scale : 0.f;
+  float o[FA_D];
+#pragma unroll
+  for (int d = 0; d < FA_D; ++d) o[d] = 0.f;
+  float m_run = -INFINITY, l_run = 0.f;
+  for (int k0 = 0; k0 < Lk; k0 += F32_BK) {
+    __syncthreads();
+    for (int idx = t; idx < F32_BK * FA_D; idx += 64) {
+      const int r = idx / FA_D, d = idx - r * FA_D;
+      const bool ok = k0 + r < Lk;
+      sK[r][d] = ok ? k[(static_cast<size_t>(b) * Lk + k0 + r) * ldk + h * FA_D + d] : 0.f;
+      sV[r][d] = ok ? v[(static_cast<size_t>(b) * Lk + k0 + r) * ldv + h * FA_D + d] : 0.f;
+    }
+    if (t < F32_BK) {
+      float add = 0.f;
+      if (k0 + t >= Lk) add = -INFINITY;
+      else if (key_mask != nullptr) add = (1.0f - key_mask[static_cast<size_t>(b) * Lk + k0 + t]) * mask_neg;
+      sM[t] = add;
+    }
+    __syncthreads();
+    float sc[F32_BK];
+    float mx = m_run;
+#pragma unroll 4
+    for (int j = 0; j < F32_BK; ++j) {
+      float a = 0.f;
+#pragma unroll
+      for (int d = 0; d < FA_D; ++d) a = fmaf(qr[d], sK[j][d], a);
+      a += sM[j];
+      sc[j] = a;
+      mx = fmaxf(mx, a);
+    }
+    // a fully masked history keeps mx = -inf only if every key so far is padding (-inf); additive finite masks never do
+    const float alpha = (m_run == -INFINITY) ? 0.f : expf(m_run - mx);
+    m_run = mx;
+    l_run *= alpha;
+#pragma unroll
+    for (int d = 0; d < FA_D; ++d) o[d] *= alpha;
+#pragma unroll 4
+    for (int j = 0; j < F32_BK; ++j) {
+      const float pj = (mx == -INFINITY) ? 0.f : expf(sc[j] - mx);
+      l_run += pj;
+#pragma unroll
+      for (int d = 0; d < FA_D; ++d) o[d] = fmaf(pj, sV[j][d], o[d]);
+    }
+  }
+  if (!active) return;
+  const float inv = 1.0f / l_run;
+  __nv_bfloat16* orow = out + (static_cast<size_t>(b) * Lq + qi) * (3 * static_cast<size_t>(width));
+#pragma unroll
+  for (int d = 0; d < FA_D; ++d) store_split1(orow, width, h * FA_D + d, o[d] * inv);
+}
+
 }  // namespace
 
 FMMT_DEFINE_WATCHDOG_ADDR(watchdog_addr_attn)
+
+cudaError_t launch_window_attention_f32(const float* qkv, __nv_bfloat16* out_split, const float* bias, const int8_t* rid,
+                                        int num_windows, int nW, int heads, int C, int N, float scale, cudaStream_t stream) {
+  if (C != heads * WA_D || N > 49 || N < 1 || num_windows <= 0) return cudaErrorInvalidValue;
+  dim3 grid(num_windows, heads);
+  window_attention_f32_kernel<<<grid, 64, 0, stream>>>(qkv, out_split, bias, rid, nW, C, N, scale);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_mha_f32(const float* q, int ldq, const float* k, int ldk, const float* v, int ldv,
+                           __nv_bfloat16* out_split, int width, const float* key_mask, float mask_neg, int B, int H, int Lq,
+                           int Lk, float scale, cudaStream_t stream) {
+  if (B <= 0 || H <= 0 || Lq <= 0 || Lk <= 0 || width < H * FA_D) return cudaErrorInvalidValue;
+  dim3 grid((Lq + 63) / 64, H, B);
+  mha_f32_kernel<<<grid, 64, 0, stream>>>(q, ldq, k, ldk, v, ldv, out_split, width, key_mask, mask_neg, Lq, Lk, scale);
+  return cudaGetLastError();
+}
 
 cudaError_t launch_window_attention(const __nv_bfloat16* qkv, __nv_bfloat16* out, const float* bias,
                                     const int8_t* rid, int num_windows, int nW, int heads, int C, int N, float scale,

@@ -27,7 +27,10 @@ struct PackError : std::runtime_error {
 }  // namespace
 
 // =================================================================================================== lifecycle
-Engine::Engine(const fmmt_config& cfg) : cfg_(cfg) {}
+Engine::Engine(const fmmt_config& cfg) : cfg_(cfg) {
+  precise_ = cfg.precision == FMMT_PRECISION_FP32;
+  kw_ = precise_ ? 3 : 1;
+}
 
 Engine::~Engine() {
   cudaDeviceSynchronize();
@@ -88,10 +91,32 @@ bf16* Engine::up_bf16(const float* src, int rows, int cols, int ld) {
   return d;
 }
 
-Lin Engine::make_lin(const float* w, const float* b, int N, int K) {
+Lin Engine::make_lin(const float* w, const float* b, int N, int K, int group) {
   Lin l;
   l.N = N; l.K = K; l.ld = round_up(K, 8);
-  l.w = up_bf16(w, N, K, l.ld);
+  if (!precise_) {
+    l.w = up_bf16(w, N, K, l.ld);
+  } else {
+    // split-bf16 x3: per group of G columns (G = ld, or the per-token width where the activation row is a concatenation
+    // of split rows, i.e. the Swin head) the stored row is [hi(G) | hi(G) | lo(G)]
+    const int G = group > 0 ? group : l.ld;
+    if (l.ld % G != 0) throw PackError("split weight: group does not divide the row");
+    std::vector<bf16> tmp(static_cast<size_t>(N) * 3 * l.ld, __float2bfloat16(0.f));
+    for (int n = 0; n < N; ++n)
+      for (int k = 0; k < K; ++k) {
+        const float x = w[static_cast<size_t>(n) * K + k];
+        const bf16 hi = __float2bfloat16(x);
+        const bf16 lo = __float2bfloat16(x - __bfloat162float(hi));
+        const size_t base = static_cast<size_t>(n) * 3 * l.ld + static_cast<size_t>(k / G) * 3 * G + (k % G);
+        tmp[base] = hi;
+        tmp[base + G] = hi;
+        tmp[base + 2 * G] = lo;
+      }
+    bf16* d = dev_alloc<bf16>(tmp.size());
+    cudaError_t e = cudaMemcpy(d, tmp.data(), tmp.size() * sizeof(bf16), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) throw PackError(std::string("cudaMemcpy failed: ") + cudaGetErrorString(e));
+    l.w = d;
+  }
   if (b) l.b = up_f32(b, N);
   return l;
 }
@@ -209,7 +234,7 @@ void Engine::pack_swin() {
       expect(bw.qkv.N == 3 * C && bw.qkv.K == C && bw.proj.N == C && bw.fc1.K == C && bw.fc2.N == C &&
                  bw.fc2.K == bw.fc1.N && bw.ln1.C == C,
              p + " dims");
-      if (C == MLP96_C && bw.fc1.N == MLP96_H && bw.fc1.b && bw.fc2.b && std::getenv("FMMT_NO_FUSED_MLP") == nullptr) {
+      if (!precise_ && C == MLP96_C && bw.fc1.N == MLP96_H && bw.fc1.b && bw.fc2.b && std::getenv("FMMT_NO_FUSED_MLP") == nullptr) {
         std::vector<bf16> img(MLP96_IMG_BYTES / sizeof(bf16));
         mlp96_pack_weights(need(p + "mlp.fc1.weight").data.data(), need(p + "mlp.fc2.weight").data.data(), img.data());
         bw.mlp_img = dev_alloc<bf16>(img.size());
@@ -280,7 +305,7 @@ void Engine::pack_swin() {
       for (int k = 0; k < K; ++k) wf[static_cast<size_t>(n) * K + k] *= sc;
       bf[n] = (b.data[n] - mu.data[n]) * sc + be.data[n];
     }
-    swin_.head = make_lin(wf.data(), bf.data(), N, K);
+    swin_.head = make_lin(wf.data(), bf.data(), N, K, C);   // fp32-grade mode: the A row is a concatenation of split token rows
   }
   {
     const HostTensor& w1 = need("linear.weight");
@@ -584,10 +609,64 @@ void Engine::gemm(GemmArgs a) {
 }
 
 void Engine::gemm_lin(const bf16* A, int lda, int M, const Lin& l, GemmArgs ep) {
-  ep.A = A; ep.lda = lda; ep.M = M;
-  ep.W = l.w; ep.ldw = l.ld; ep.N = l.N; ep.K = l.K;
+  ep.A = A; ep.lda = lda * kw_; ep.M = M;
+  ep.W = l.w; ep.ldw = l.ld * kw_; ep.N = l.N; ep.K = precise_ ? 3 * l.ld : l.K;
   ep.bias = l.b;
+  if (precise_ && lda != l.ld && first_err_ == cudaSuccess && !arena_.dry()) {
+    first_err_ = cudaErrorInvalidValue;
+    err_ = "fp32-grade mode: activation pitch must equal the padded weight pitch";
+    return;
+  }
   gemm(ep);
+}
+
+void Engine::split16(const float* in, int ld_in, bf16* out, int ldp, int M, int C) {
+  if (arena_.dry() || first_err_ != cudaSuccess) return;
+  count_launch();
+  cudaEvent_t e1 = nullptr;
+  if (prof_) e1 = prof_begin("split_bf16", 0.0, static_cast<double>(M) * C * 4.0 + static_cast<double>(M) * ldp * 6.0);
+  ck(launch_split_bf16(in, ld_in, out, ldp, M, C, st_), "split_bf16");
+  if (prof_) prof_end(e1);
+}
+
+void Engine::lin_to_operand(const bf16* A, int lda, int M, const Lin& l, int act, bf16* out16) {
+  GemmArgs g;
+  g.act = act;
+  if (!precise_) {
+    g.out_bf16 = out16; g.ldo16 = l.N;
+    gemm_lin(A, lda, M, l, g);
+    return;
+  }
+  const size_t mk = arena_.mark();
+  float* t = arena_.alloc<float>(static_cast<size_t>(M) * l.N);
+  g.out_f32 = t; g.ldo32 = l.N;
+  gemm_lin(A, lda, M, l, g);
+  split16(t, l.N, out16, l.N, M, l.N);
+  arena_.release(mk);   // stream order keeps the scratch alive until the split has read it
+}
+
+void Engine::lin_to_attn(const bf16* A, int lda, int M, const Lin& l, void* out) {
+  GemmArgs g;
+  if (!precise_) { g.out_bf16 = static_cast<bf16*>(out); g.ldo16 = l.N; }
+  else { g.out_f32 = static_cast<float*>(out); g.ldo32 = l.N; }
+  gemm_lin(A, lda, M, l, g);
+}
+
+void Engine::attn_mha(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv, bf16* out, int width,
+                      const float* key_mask, float mask_neg, int B, int H, int Lq, int Lk, const std::string& key) {
+  if (arena_.dry() || first_err_ != cudaSuccess) return;
+  count_launch();
+  const double fl = 4.0 * B * static_cast<double>(Lq) * Lk * H * 64.0;
+  flops_ += fl;
+  cudaEvent_t e1 = nullptr;
+  if (prof_) e1 = prof_begin(key, fl, attn_esize() * 64.0 * H * B * (2.0 * Lq + 2.0 * Lk));
+  if (!precise_)
+    ck(launch_mha(static_cast<const bf16*>(q), ldq, static_cast<const bf16*>(k), ldk, static_cast<const bf16*>(v), ldv, out,
+                  width, key_mask, mask_neg, B, H, Lq, Lk, 0.125f, st_), "mha");
+  else
+    ck(launch_mha_f32(static_cast<const float*>(q), ldq, static_cast<const float*>(k), ldk, static_cast<const float*>(v), ldv,
+                      out, width, key_mask, mask_neg, B, H, Lq, Lk, 0.125f, st_), "mha_f32");
+  if (prof_) prof_end(e1);
 }
 
 void Engine::ln(LnArgs a) {
@@ -705,13 +784,13 @@ void Engine::capture_block(const std::string& name, const SwinStageW& sw, const 
   ck(launch_gather_rows(x, bw.to_natural, T, sw.C, nf * T, it->second.dst + off, st_), "capture gather");
 }
 
-void Engine::swin_block(const SwinStageW& sw, const SwinBlockW& bw, float*& x, float*& xalt, int nf, bf16* h, bf16* qkv,
+void Engine::swin_block(const SwinStageW& sw, const SwinBlockW& bw, float*& x, float*& xalt, int nf, bf16* h, void* qkv,
                         bf16* a, bf16* hid) {
   const int T = sw.R * sw.R, C = sw.C, M = nf * T;
   LnArgs l1;
   l1.in = x; l1.ld_in = C; l1.M = M; l1.nseg = 1; l1.cseg = C;
   l1.gamma = bw.ln1.g; l1.beta = bw.ln1.b; l1.eps = 1e-5f;
-  l1.out_bf16 = h; l1.ld16 = C;
+  l1.out_bf16 = h; l1.ld16 = C * kw_; l1.split = precise_;
   if (!bw.identity) {
     // norm1 + roll + window_partition as ONE row gather; the gathered raw rows become the new residual stream
     l1.map = bw.gather; l1.map_period = T; l1.src_period = T;
@@ -719,17 +798,20 @@ void Engine::swin_block(const SwinStageW& sw, const SwinBlockW& bw, float*& x, f
   }
   ln(l1);
   if (!bw.identity) std::swap(x, xalt);
-  GemmArgs g1;
-  g1.out_bf16 = qkv; g1.ldo16 = 3 * C;
-  gemm_lin(h, C, M, bw.qkv, g1);                                    // qkv Linear
+  lin_to_attn(h, C, M, bw.qkv, qkv);                                 // qkv Linear
   if (!arena_.dry() && first_err_ == cudaSuccess) {
     count_launch();
     flops_ += 4.0 * M * sw.N * C;
     cudaEvent_t e1 = nullptr;
-    if (prof_) e1 = prof_begin("window_attention C=" + std::to_string(C), 4.0 * M * sw.N * C, 8.0 * M * C);
-    ck(launch_window_attention(qkv, a, bw.bias_exp, bw.shift ? sw.rid : nullptr, nf * sw.nW, sw.nW, sw.heads, C, sw.N,
-                               1.0f / std::sqrt(32.0f), st_),
-       "window_attention");
+    if (prof_) e1 = prof_begin("window_attention C=" + std::to_string(C), 4.0 * M * sw.N * C, 4.0 * attn_esize() * M * C);
+    if (!precise_)
+      ck(launch_window_attention(static_cast<const bf16*>(qkv), a, bw.bias_exp, bw.shift ? sw.rid : nullptr, nf * sw.nW,
+                                 sw.nW, sw.heads, C, sw.N, 1.0f / std::sqrt(32.0f), st_),
+         "window_attention");
+    else
+      ck(launch_window_attention_f32(static_cast<const float*>(qkv), a, bw.bias_exp, bw.shift ? sw.rid : nullptr,
+                                     nf * sw.nW, sw.nW, sw.heads, C, sw.N, 1.0f / std::sqrt(32.0f), st_),
+         "window_attention_f32");
     if (prof_) prof_end(e1);
   }
   GemmArgs g2;                                                      // proj + shortcut, in window order (no scatter)
@@ -740,18 +822,16 @@ void Engine::swin_block(const SwinStageW& sw, const SwinBlockW& bw, float*& x, f
     return;
   }
   static const bool no_stream = std::getenv("FMMT_NO_MLP_STREAM") != nullptr;
-  if (!no_stream && mlp_stream_supported(C, bw.fc1.N) && bw.fc1.b && bw.fc2.b) {   // stages 2-3: same, weights streamed
+  if (!precise_ && !no_stream && mlp_stream_supported(C, bw.fc1.N) && bw.fc1.b && bw.fc2.b) {   // stages 2-3: same, weights streamed
     mlp_stream(x, M, C, bw);
     return;
   }
   LnArgs l2;
   l2.in = x; l2.ld_in = C; l2.M = M; l2.cseg = C;
   l2.gamma = bw.ln2.g; l2.beta = bw.ln2.b; l2.eps = 1e-5f;
-  l2.out_bf16 = h; l2.ld16 = C;
+  l2.out_bf16 = h; l2.ld16 = C * kw_; l2.split = precise_;
   ln(l2);                                                           // norm2
-  GemmArgs g3;
-  g3.act = ACT_GELU; g3.out_bf16 = hid; g3.ldo16 = bw.fc1.N;
-  gemm_lin(h, C, M, bw.fc1, g3);                                    // fc1 + GELU
+  lin_to_operand(h, C, M, bw.fc1, ACT_GELU, hid);                   // fc1 + GELU
   GemmArgs g4;
   g4.residual = x; g4.ldr = C; g4.out_f32 = x; g4.ldo32 = C;
   gemm_lin(hid, bw.fc1.N, M, bw.fc2, g4);                           // fc2 + residual
@@ -765,15 +845,15 @@ void Engine::swin_early(const float* frames, int f0, int nf, float* x_out) {
   const SwinStageW& s0 = swin_.stages[0];
   const int T0 = s0.R * s0.R, C0 = s0.C;
   int M = nf * T0;
-  bf16* col = arena_.alloc<bf16>(static_cast<size_t>(M) * 48);
+  bf16* col = arena_.alloc<bf16>(static_cast<size_t>(M) * 48 * kw_);
   float* x = (split == 0) ? x_out : arena_.alloc<float>(static_cast<size_t>(M) * C0);
   float* xalt = (split == 0) ? nullptr : arena_.alloc<float>(static_cast<size_t>(M) * C0);
-  bf16* h = arena_.alloc<bf16>(static_cast<size_t>(M) * C0);
-  bf16* qkv = arena_.alloc<bf16>(static_cast<size_t>(M) * 3 * C0);
-  bf16* a = arena_.alloc<bf16>(static_cast<size_t>(M) * C0);
-  bf16* hid = arena_.alloc<bf16>(static_cast<size_t>(M) * c.mlp_ratio * C0);
+  bf16* h = arena_.alloc<bf16>(static_cast<size_t>(M) * C0 * kw_);
+  void* qkv = arena_.alloc<char>(static_cast<size_t>(M) * 3 * C0 * attn_esize());
+  bf16* a = arena_.alloc<bf16>(static_cast<size_t>(M) * C0 * kw_);
+  bf16* hid = arena_.alloc<bf16>(static_cast<size_t>(M) * c.mlp_ratio * C0 * kw_);
   const size_t frame_elems = static_cast<size_t>(3) * c.img_size * c.img_size;
-  OP(launch_patch_im2col(frames + static_cast<size_t>(f0) * frame_elems, col, nf, c.img_size, c.img_size, st_), "im2col");
+  OP(launch_patch_im2col(frames + static_cast<size_t>(f0) * frame_elems, col, nf, c.img_size, c.img_size, precise_, st_), "im2col");
   GemmArgs g;
   g.out_f32 = x; g.ldo32 = C0;
   gemm_lin(col, 48, M, swin_.patch, g);                              // Conv2d(3,96,k4,s4) as GEMM (K = 48)
@@ -794,7 +874,7 @@ void Engine::swin_early(const float* frames, int f0, int nf, float* x_out) {
     lm.in = x; lm.ld_in = sw.C; lm.M = nf * T / 4; lm.nseg = 4; lm.cseg = sw.C;
     lm.map = sw.merge_map; lm.map_period = T / 4; lm.src_period = T;
     lm.gamma = sw.merge_ln.g; lm.beta = sw.merge_ln.b; lm.eps = 1e-5f;
-    lm.out_bf16 = h; lm.ld16 = 4 * sw.C;
+    lm.out_bf16 = h; lm.ld16 = 4 * sw.C * kw_; lm.split = precise_;
     ln(lm);
     GemmArgs gm;
     float* dst = (li == split - 1) ? x_out : x;
@@ -809,10 +889,10 @@ void Engine::swin_late(float* x, int f0, int nf, bf16* feat_ln) {
   const SwinStageW& s0 = swin_.stages[split];
   const size_t M0 = static_cast<size_t>(nf) * s0.R * s0.R;
   float* xalt = arena_.alloc<float>(M0 * s0.C);
-  bf16* h = arena_.alloc<bf16>(M0 * s0.C);
-  bf16* qkv = arena_.alloc<bf16>(M0 * 3 * s0.C);
-  bf16* a = arena_.alloc<bf16>(M0 * s0.C);
-  bf16* hid = arena_.alloc<bf16>(M0 * c.mlp_ratio * s0.C);
+  bf16* h = arena_.alloc<bf16>(M0 * s0.C * kw_);
+  void* qkv = arena_.alloc<char>(M0 * 3 * s0.C * attn_esize());
+  bf16* a = arena_.alloc<bf16>(M0 * s0.C * kw_);
+  bf16* hid = arena_.alloc<bf16>(M0 * c.mlp_ratio * s0.C * kw_);
   for (int li = split; li < c.num_stages; ++li) {
     const SwinStageW& sw = swin_.stages[li];
     const int T = sw.R * sw.R;
@@ -825,7 +905,7 @@ void Engine::swin_late(float* x, int f0, int nf, bf16* feat_ln) {
       lm.in = x; lm.ld_in = sw.C; lm.M = nf * T / 4; lm.nseg = 4; lm.cseg = sw.C;
       lm.map = sw.merge_map; lm.map_period = T / 4; lm.src_period = T;
       lm.gamma = sw.merge_ln.g; lm.beta = sw.merge_ln.b; lm.eps = 1e-5f;
-      lm.out_bf16 = h; lm.ld16 = 4 * sw.C;
+      lm.out_bf16 = h; lm.ld16 = 4 * sw.C * kw_; lm.split = precise_;
       ln(lm);
       GemmArgs gm;
       gm.out_f32 = x; gm.ldo32 = 2 * sw.C;
@@ -838,7 +918,7 @@ void Engine::swin_late(float* x, int f0, int nf, bf16* feat_ln) {
   lf.in = x; lf.ld_in = sl.C; lf.M = nf * Tl; lf.cseg = sl.C;
   if (swin_.final_gather != nullptr) { lf.map = swin_.final_gather; lf.map_period = Tl; lf.src_period = Tl; }
   lf.gamma = swin_.head_ln.g; lf.beta = swin_.head_ln.b; lf.eps = 1e-5f;
-  lf.out_bf16 = feat_ln + static_cast<size_t>(f0) * Tl * sl.C; lf.ld16 = sl.C;
+  lf.out_bf16 = feat_ln + static_cast<size_t>(f0) * Tl * sl.C * kw_; lf.ld16 = sl.C * kw_; lf.split = precise_;
   ln(lf);
 }
 
@@ -848,12 +928,13 @@ void Engine::swin_body(const float* frames, int F, const float* gumbel, float ta
   const int split = swin_split(c);
   const SwinStageW& sl = swin_.stages.back();
   const size_t FL = static_cast<size_t>(sl.R) * sl.R * sl.C;
-  bf16* feat_ln = arena_.alloc<bf16>(static_cast<size_t>(F) * FL);
+  bf16* feat_ln = arena_.alloc<bf16>(static_cast<size_t>(F) * FL * kw_);
   float* feat512 = arena_.alloc<float>(static_cast<size_t>(F) * c.feat_dim);
   // Frames per pass: measured on B200 (profiles/r01_chunk_sweep.txt). With persistent kernels bigger passes win (fewer
   // launches, fewer partial waves): 64/160 -> 196 utt/s, 96/192 -> 217, 320/640 -> 234, 320/1280 -> 239, 1280/1280 -> 236.
-  const int big = c.swin_chunk_late > 0 ? c.swin_chunk_late : 1280;
-  const int small = c.swin_chunk > 0 ? c.swin_chunk : 320;
+  // (fp32-grade mode keeps fp32 intermediates and split operands, 3-4x the bytes per frame: smaller passes)
+  const int big = c.swin_chunk_late > 0 ? c.swin_chunk_late : (precise_ ? 320 : 1280);
+  const int small = c.swin_chunk > 0 ? c.swin_chunk : (precise_ ? 80 : 320);
   const SwinStageW& ss = swin_.stages[split];
   const size_t per_frame_split = static_cast<size_t>(ss.R) * ss.R * ss.C;
   for (int f0 = 0; f0 < F; f0 += big) {
@@ -893,34 +974,23 @@ int Engine::swin_forward(const float* frames, int F, const float* gumbel, float 
 void Engine::enc_layers(const std::vector<EncLayerW>& layers, float* x32, bf16* x16, int U, int L, int H, int heads,
                         int ffn, const float* mask01, float mask_neg, float eps) {
   const int M = U * L;
-  bf16* qkv = arena_.alloc<bf16>(static_cast<size_t>(M) * 3 * H);
-  bf16* ctx = arena_.alloc<bf16>(static_cast<size_t>(M) * H);
-  bf16* hid = arena_.alloc<bf16>(static_cast<size_t>(M) * ffn);
+  char* qkv = arena_.alloc<char>(static_cast<size_t>(M) * 3 * H * attn_esize());
+  bf16* ctx = arena_.alloc<bf16>(static_cast<size_t>(M) * H * kw_);
+  bf16* hid = arena_.alloc<bf16>(static_cast<size_t>(M) * ffn * kw_);
+  const size_t es = attn_esize();
   for (const EncLayerW& l : layers) {
-    GemmArgs g1;
-    g1.out_bf16 = qkv; g1.ldo16 = 3 * H;
-    gemm_lin(x16, H, M, l.qkv, g1);
-    if (!arena_.dry() && first_err_ == cudaSuccess) {
-      count_launch();
-      flops_ += 4.0 * U * static_cast<double>(L) * L * H;
-      cudaEvent_t e1 = nullptr;
-      if (prof_) e1 = prof_begin("mha H=" + std::to_string(H) + " L=" + std::to_string(L),
-                                 4.0 * U * static_cast<double>(L) * L * H, 8.0 * M * H);
-      ck(launch_mha(qkv, 3 * H, qkv + H, 3 * H, qkv + 2 * H, 3 * H, ctx, H, mask01, mask_neg, U, heads, L, L, 0.125f, st_),
-         "mha");
-      if (prof_) prof_end(e1);
-    }
+    lin_to_attn(x16, H, M, l.qkv, qkv);
+    attn_mha(qkv, 3 * H, qkv + es * H, 3 * H, qkv + es * 2 * H, 3 * H, ctx, H, mask01, mask_neg, U, heads, L, L,
+             "mha H=" + std::to_string(H) + " L=" + std::to_string(L));
     GemmArgs g2;
     g2.residual = x32; g2.ldr = H; g2.out_f32 = x32; g2.ldo32 = H;
     gemm_lin(ctx, H, M, l.o, g2);
     LnArgs n1;
     n1.in = x32; n1.ld_in = H; n1.M = M; n1.cseg = H;
     n1.gamma = l.ln1.g; n1.beta = l.ln1.b; n1.eps = eps;
-    n1.out_f32 = x32; n1.ld32 = H; n1.out_bf16 = x16; n1.ld16 = H;
+    n1.out_f32 = x32; n1.ld32 = H; n1.out_bf16 = x16; n1.ld16 = H * kw_; n1.split = precise_;
     ln(n1);
-    GemmArgs g3;
-    g3.act = ACT_GELU; g3.out_bf16 = hid; g3.ldo16 = ffn;
-    gemm_lin(x16, H, M, l.fc1, g3);
+    lin_to_operand(x16, H, M, l.fc1, ACT_GELU, hid);
     GemmArgs g4;
     g4.residual = x32; g4.ldr = H; g4.out_f32 = x32; g4.ldo32 = H;
     gemm_lin(hid, ffn, M, l.fc2, g4);
@@ -934,12 +1004,15 @@ void Engine::meld_encoder(const MeldEncW& m, const float* in, int in_dim, int U,
                           bf16* x16) {
   const int H = cfg_.hidden, M = U * L;
   const int ldp = round_up(in_dim, 8);
-  bf16* in16 = arena_.alloc<bf16>(static_cast<size_t>(M) * ldp);
-  OP(launch_cast_bf16(in, in_dim, in16, ldp, M, in_dim, st_), "cast");
+  bf16* in16 = arena_.alloc<bf16>(static_cast<size_t>(M) * ldp * kw_);
+  if (!precise_) OP(launch_cast_bf16(in, in_dim, in16, ldp, M, in_dim, st_), "cast");
+  else split16(in, in_dim, in16, ldp, M, in_dim);
   GemmArgs g;                                    // Linear(in,768) + learned positions (Transformer.py:213-217)
   g.residual = m.pos; g.ldr = H; g.res_mod = L;
-  g.out_f32 = x32; g.ldo32 = H; g.out_bf16 = x16; g.ldo16 = H;
+  g.out_f32 = x32; g.ldo32 = H;
+  if (!precise_) { g.out_bf16 = x16; g.ldo16 = H; }
   gemm_lin(in16, ldp, M, m.in, g);
+  if (precise_) split16(x32, H, x16, H, M, H);
   enc_layers(m.layers, x32, x16, U, L, H, cfg_.heads, cfg_.ffn, mask01, -10000.0f, cfg_.eps);
 }
 
@@ -948,14 +1021,15 @@ void Engine::cmt_encoder(const CmtW& cw, const float* xq, int Lq, int q_total, i
   const int H = cfg_.hidden;
   const int Mq = U * Lq, Mk = U * Lk;
   const size_t mark = arena_.mark();
+  const size_t es = attn_esize();
   float* x = arena_.alloc<float>(static_cast<size_t>(Mq) * H);
   float* ek = arena_.alloc<float>(static_cast<size_t>(Mk) * H);
-  bf16* qn = arena_.alloc<bf16>(static_cast<size_t>(Mq) * H);
-  bf16* kn = arena_.alloc<bf16>(static_cast<size_t>(Mk) * H);
-  bf16* q = arena_.alloc<bf16>(static_cast<size_t>(Mq) * H);
-  bf16* kv = arena_.alloc<bf16>(static_cast<size_t>(Mk) * 2 * H);
-  bf16* a = arena_.alloc<bf16>(static_cast<size_t>(Mq) * H);
-  bf16* hid = arena_.alloc<bf16>(static_cast<size_t>(Mq) * 4 * H);
+  bf16* qn = arena_.alloc<bf16>(static_cast<size_t>(Mq) * H * kw_);
+  bf16* kn = arena_.alloc<bf16>(static_cast<size_t>(Mk) * H * kw_);
+  char* q = arena_.alloc<char>(static_cast<size_t>(Mq) * H * es);
+  char* kv = arena_.alloc<char>(static_cast<size_t>(Mk) * 2 * H * es);
+  bf16* a = arena_.alloc<bf16>(static_cast<size_t>(Mq) * H * kw_);
+  bf16* hid = arena_.alloc<bf16>(static_cast<size_t>(Mq) * 4 * H * kw_);
   const float scale = std::sqrt(static_cast<float>(H));
   OP(launch_cmt_embed(xq, Lq, q_total, q_off, sinusoid_, U, Lq, H, scale, x, st_), "cmt_embed");
   OP(launch_cmt_embed(xkv, Lk, kv_total, kv_off, sinusoid_, U, Lk, H, scale, ek, st_), "cmt_embed");
@@ -963,35 +1037,22 @@ void Engine::cmt_encoder(const CmtW& cw, const float* xq, int Lq, int q_total, i
     LnArgs nq;
     nq.in = x; nq.ld_in = H; nq.M = Mq; nq.cseg = H;
     nq.gamma = l.ln0.g; nq.beta = l.ln0.b; nq.eps = 1e-5f;
-    nq.out_bf16 = qn; nq.ld16 = H;
+    nq.out_bf16 = qn; nq.ld16 = H * kw_; nq.split = precise_;
     ln(nq);
     LnArgs nk = nq;                                  // K/V streams use the same layer_norms[0] (:145-148)
     nk.in = ek; nk.M = Mk; nk.out_bf16 = kn;
     ln(nk);
-    GemmArgs gq;
-    gq.out_bf16 = q; gq.ldo16 = H;
-    gemm_lin(qn, H, Mq, l.q, gq);
-    GemmArgs gk;
-    gk.out_bf16 = kv; gk.ldo16 = 2 * H;
-    gemm_lin(kn, H, Mk, l.kv, gk);
-    if (!arena_.dry() && first_err_ == cudaSuccess) {
-      count_launch();
-      flops_ += 4.0 * U * static_cast<double>(Lq) * Lk * H;
-      cudaEvent_t e1 = nullptr;
-      if (prof_) e1 = prof_begin("mha cross Lq=" + std::to_string(Lq) + " Lk=" + std::to_string(Lk),
-                                 4.0 * U * static_cast<double>(Lq) * Lk * H, 2.0 * H * (2.0 * Mq + 2.0 * Mk));
-      ck(launch_mha(q, H, kv, 2 * H, kv + H, 2 * H, a, H, nullptr, 0.f, U, cw.heads, Lq, Lk, 0.125f, st_), "mha");
-      if (prof_) prof_end(e1);
-    }
+    lin_to_attn(qn, H, Mq, l.q, q);
+    lin_to_attn(kn, H, Mk, l.kv, kv);
+    attn_mha(q, H, kv, 2 * H, kv + es * H, 2 * H, a, H, nullptr, 0.f, U, cw.heads, Lq, Lk,
+             "mha cross Lq=" + std::to_string(Lq) + " Lk=" + std::to_string(Lk));
     GemmArgs go;
     go.residual = x; go.ldr = H; go.out_f32 = x; go.ldo32 = H;
     gemm_lin(a, H, Mq, l.o, go);
     LnArgs n1 = nq;
     n1.gamma = l.ln1.g; n1.beta = l.ln1.b;
     ln(n1);
-    GemmArgs g1;
-    g1.act = ACT_GELU; g1.out_bf16 = hid; g1.ldo16 = 4 * H;
-    gemm_lin(qn, H, Mq, l.fc1, g1);
+    lin_to_operand(qn, H, Mq, l.fc1, ACT_GELU, hid);
     GemmArgs g2;
     g2.residual = x; g2.ldr = H; g2.out_f32 = x; g2.ldo32 = H;
     gemm_lin(hid, 4 * H, Mq, l.fc2, g2);
@@ -999,7 +1060,7 @@ void Engine::cmt_encoder(const CmtW& cw, const float* xq, int Lq, int q_total, i
   LnArgs nf;
   nf.in = x; nf.ld_in = H; nf.M = Mq; nf.cseg = H;
   nf.gamma = cw.final_ln.g; nf.beta = cw.final_ln.b; nf.eps = 1e-5f;
-  nf.out_f32 = out32; nf.ld32 = H; nf.out_bf16 = out16; nf.ld16 = H;
+  nf.out_f32 = out32; nf.ld32 = H; nf.out_bf16 = out16; nf.ld16 = H * kw_; nf.split = precise_;
   nf.rows_in = Lq; nf.rows_out = out_total; nf.row_off = out_off;
   ln(nf);
   arena_.release(mark);
@@ -1007,11 +1068,15 @@ void Engine::cmt_encoder(const CmtW& cw, const float* xq, int Lq, int q_total, i
 
 void Engine::pool_head(const float* x32, const bf16* x16, const float* mask01, int U, int L, float* logits) {
   const int H = cfg_.hidden;
-  bf16* th = arena_.alloc<bf16>(static_cast<size_t>(U) * L * H);
+  char* th = arena_.alloc<char>(static_cast<size_t>(U) * L * H * attn_esize());
   GemmArgs g;
-  g.act = ACT_TANH; g.out_bf16 = th; g.ldo16 = H;
+  g.act = ACT_TANH;
+  if (!precise_) { g.out_bf16 = reinterpret_cast<bf16*>(th); g.ldo16 = H; }
+  else { g.out_f32 = reinterpret_cast<float*>(th); g.ldo32 = H; }
   gemm_lin(x16, H, U * L, pool_.P, g);
-  OP(launch_pool_classify(x32, th, mask01, pool_.wv, pool_.bv, pool_.wc, pool_.bc, U, L, H, cfg_.num_labels, logits, st_),
+  OP(launch_pool_classify(x32, precise_ ? nullptr : reinterpret_cast<const bf16*>(th),
+                          precise_ ? reinterpret_cast<const float*>(th) : nullptr, mask01, pool_.wv, pool_.bv, pool_.wc,
+                          pool_.bc, U, L, H, cfg_.num_labels, logits, st_),
      "pool_classify");
 }
 
@@ -1024,12 +1089,12 @@ void Engine::multimodal_body(const int64_t* ids, const int64_t* mask, const int6
   // ---- text (src/models.py:99-107)
   int* pos = arena_.alloc<int>(M);
   float* tx32 = arena_.alloc<float>(static_cast<size_t>(M) * D);
-  bf16* tx16 = arena_.alloc<bf16>(static_cast<size_t>(M) * D);
+  bf16* tx16 = arena_.alloc<bf16>(static_cast<size_t>(M) * D * kw_);
   float* tmask = arena_.alloc<float>(M);
   if (!arena_.dry() && first_err_ == cudaSuccess) {
     count_launch(2);
     ck(launch_text_embed(ids, pos, U, L, c.text_kind == FMMT_TEXT_ROBERTA, c.pad_id, text_.word, text_.pos, text_.type0,
-                         c.max_pos, c.vocab_size, text_.emb_ln.g, text_.emb_ln.b, c.text_eps, D, tx32, tx16, st_),
+                         c.max_pos, c.vocab_size, text_.emb_ln.g, text_.emb_ln.b, c.text_eps, D, tx32, tx16, precise_, st_),
        "text_embed");
   }
   OP(launch_cast_i64_f32(mask, tmask, M, st_), "mask cast");
@@ -1050,9 +1115,9 @@ void Engine::multimodal_body(const int64_t* ids, const int64_t* mask, const int6
   capture("mm.text", txt, static_cast<size_t>(U) * Lt * H);
   // ---- audio / vision self-attention encoders (src/models.py:154-166)
   float* ax32 = arena_.alloc<float>(static_cast<size_t>(U) * La * H);
-  bf16* ax16 = arena_.alloc<bf16>(static_cast<size_t>(U) * La * H);
+  bf16* ax16 = arena_.alloc<bf16>(static_cast<size_t>(U) * La * H * kw_);
   float* vx32 = arena_.alloc<float>(static_cast<size_t>(U) * Lv * H);
-  bf16* vx16 = arena_.alloc<bf16>(static_cast<size_t>(U) * Lv * H);
+  bf16* vx16 = arena_.alloc<bf16>(static_cast<size_t>(U) * Lv * H * kw_);
   {
     const size_t mk = arena_.mark();
     meld_encoder(audio_, audio, c.audio_dim, U, La, audio_mask, ax32, ax16);
@@ -1066,7 +1131,7 @@ void Engine::multimodal_body(const int64_t* ids, const int64_t* mask, const int6
   const int Lta = Lt + La, Ltot = Lta + Lv;
   float* ta = arena_.alloc<float>(static_cast<size_t>(U) * Lta * H);
   float* fused = arena_.alloc<float>(static_cast<size_t>(U) * Ltot * H);
-  bf16* fused16 = arena_.alloc<bf16>(static_cast<size_t>(U) * Ltot * H);
+  bf16* fused16 = arena_.alloc<bf16>(static_cast<size_t>(U) * Ltot * H * kw_);
   float* fmask = arena_.alloc<float>(static_cast<size_t>(U) * Ltot);
   cmt_encoder(cmt_ta_, txt, Lt, Lt, 0, ax32, La, La, 0, U, ta, nullptr, Lta, 0);
   cmt_encoder(cmt_ta_, ax32, La, La, 0, txt, Lt, Lt, 0, U, ta, nullptr, Lta, Lt);
@@ -1093,7 +1158,7 @@ void Engine::unimodal_body(const float* inputs, const float* mask, int U, float*
   const fmmt_config& c = cfg_;
   const int H = c.hidden, Lv = c.vision_len;
   float* x32 = arena_.alloc<float>(static_cast<size_t>(U) * Lv * H);
-  bf16* x16 = arena_.alloc<bf16>(static_cast<size_t>(U) * Lv * H);
+  bf16* x16 = arena_.alloc<bf16>(static_cast<size_t>(U) * Lv * H * kw_);
   const size_t mk = arena_.mark();
   meld_encoder(vision_, inputs, c.vision_dim, U, Lv, mask, x32, x16);
   arena_.release(mk);

@@ -30,6 +30,8 @@ struct HostTensor {
 };
 
 // Linear weight on device: bf16 [N, ld] (K contiguous, ld = K rounded up to 8, zero padded) + fp32 bias.
+// fp32-grade mode (fmmt_config.precision = 1): bf16 [N, 3*ld] = [hi | hi | lo] per group of `ld` columns, so that with the
+// activation stored as [hi | lo | hi] the K' = 3K product is A_hi W_hi + A_lo W_hi + A_hi W_lo (16 mantissa bits per operand).
 struct Lin {
   bf16* w = nullptr;
   float* b = nullptr;
@@ -164,7 +166,7 @@ class Engine {
   template <typename T> T* dev_alloc(size_t n);
   float* up_f32(const float* src, size_t n);
   bf16* up_bf16(const float* src, int rows, int cols, int ld);
-  Lin make_lin(const float* w, const float* b, int N, int K);
+  Lin make_lin(const float* w, const float* b, int N, int K, int group = 0);
   Lin lin(const std::string& prefix, bool bias = true);
   Norm norm(const std::string& prefix);
   EncLayerW enc_layer(const std::string& qkv_prefix, const std::string& o_prefix, const std::string& ln1_prefix,
@@ -181,6 +183,14 @@ class Engine {
   // ---- op wrappers (no-ops while sizing the workspace)
   void gemm(GemmArgs a);
   void gemm_lin(const bf16* A, int lda, int M, const Lin& l, GemmArgs ep);
+  // Linear whose output is the A operand of a later Linear: bf16 [M, N] (bf16 mode) or split bf16 [M, 3N] through an
+  // fp32 scratch (fp32-grade mode)
+  void lin_to_operand(const bf16* A, int lda, int M, const Lin& l, int act, bf16* out16);
+  // Linear whose output feeds an attention core: bf16 [M, N] or fp32 [M, N] (fp32-grade mode); `out` is sized for either
+  void lin_to_attn(const bf16* A, int lda, int M, const Lin& l, void* out);
+  void attn_mha(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv, bf16* out, int width,
+                const float* key_mask, float mask_neg, int B, int H, int Lq, int Lk, const std::string& key);
+  void split16(const float* in, int ld_in, bf16* out, int ldp, int M, int C);
   void ln(LnArgs a);
   void mlp96(float* x, int M, const SwinBlockW& bw);
   void mlp_stream(float* x, int M, int C, const SwinBlockW& bw);
@@ -192,7 +202,7 @@ class Engine {
                  float* importance, float* feat);
   void swin_early(const float* frames, int f0, int nf, float* x2_out);
   void swin_late(float* x2, int f0, int nf, bf16* feat_ln);
-  void swin_block(const SwinStageW& sw, const SwinBlockW& bw, float*& x, float*& xalt, int nf, bf16* h, bf16* qkv,
+  void swin_block(const SwinStageW& sw, const SwinBlockW& bw, float*& x, float*& xalt, int nf, bf16* h, void* qkv,
                   bf16* a, bf16* hid);
   void capture_block(const std::string& name, const SwinStageW& sw, const SwinBlockW& bw, const float* x, int nf, int f0);
   void enc_layers(const std::vector<EncLayerW>& layers, float* x32, bf16* x16, int U, int L, int H, int heads, int ffn,
@@ -209,6 +219,9 @@ class Engine {
   template <typename Fn> int run(Fn&& body, cudaStream_t st);
 
   fmmt_config cfg_;
+  bool precise_ = false;   // fp32-grade mode (cfg.precision == 1)
+  int kw_ = 1;             // operand width multiplier: 3 in fp32-grade mode (split-bf16 x3), else 1
+  size_t attn_esize() const { return precise_ ? sizeof(float) : sizeof(bf16); }
   bool finalized_ = false;
   std::unordered_map<std::string, HostTensor> host_;
   std::vector<void*> dev_ptrs_;

@@ -29,7 +29,20 @@ struct LnParams {
   float* out_f32; int ld32; __nv_bfloat16* out_bf16; int ld16;
   int rows_in, rows_out, row_off;
   float* out_raw; int ld_raw;
+  int split;   // fp32-grade mode: the bf16 output row is [hi | lo | hi] (3C wide), hi = bf16(y), lo = bf16(y - hi)
 };
+
+// Split-bf16 operand of the fp32-grade mode: with weights stored as [hi | hi | lo] the K' = 3K product is
+// A_hi W_hi + A_lo W_hi + A_hi W_lo, i.e. both operands carry 16 mantissa bits (the dropped lo*lo term is 2^-18 relative).
+__device__ __forceinline__ void store_split4(__nv_bfloat16* row, int C, int col, float4 y) {
+  const __nv_bfloat16 h0 = __float2bfloat16(y.x), h1 = __float2bfloat16(y.y), h2 = __float2bfloat16(y.z), h3 = __float2bfloat16(y.w);
+  const uint2 hi = make_uint2(pack_bf16(__bfloat162float(h0), __bfloat162float(h1)), pack_bf16(__bfloat162float(h2), __bfloat162float(h3)));
+  const uint2 lo = make_uint2(pack_bf16(y.x - __bfloat162float(h0), y.y - __bfloat162float(h1)),
+                              pack_bf16(y.z - __bfloat162float(h2), y.w - __bfloat162float(h3)));
+  *reinterpret_cast<uint2*>(row + col) = hi;
+  *reinterpret_cast<uint2*>(row + C + col) = lo;
+  *reinterpret_cast<uint2*>(row + 2 * C + col) = hi;
+}
 
 __global__ void __launch_bounds__(256) layernorm_kernel(const LnParams a) {
   const int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -86,8 +99,10 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const LnParams a) {
       y.z = (v[t].z - mean) * rstd * g.z + b.z;
       y.w = (v[t].w - mean) * rstd * g.w + b.w;
       if (a.out_f32 != nullptr) *reinterpret_cast<float4*>(a.out_f32 + dest * a.ld32 + i * 4) = y;
-      if (a.out_bf16 != nullptr)
-        *reinterpret_cast<uint2*>(a.out_bf16 + dest * a.ld16 + i * 4) = make_uint2(pack_bf16(y.x, y.y), pack_bf16(y.z, y.w));
+      if (a.out_bf16 != nullptr) {
+        if (a.split) store_split4(a.out_bf16 + dest * a.ld16, C, i * 4, y);
+        else *reinterpret_cast<uint2*>(a.out_bf16 + dest * a.ld16 + i * 4) = make_uint2(pack_bf16(y.x, y.y), pack_bf16(y.z, y.w));
+      }
       if (a.out_raw != nullptr) *reinterpret_cast<float4*>(a.out_raw + static_cast<long long>(r) * a.ld_raw + i * 4) = v[t];
     }
   }
@@ -153,8 +168,10 @@ __global__ void __launch_bounds__(256) layernorm_vec_kernel(const LnParams a) {
     y.z = (v[t].z - mean) * rstd * g.z + b.z;
     y.w = (v[t].w - mean) * rstd * g.w + b.w;
     if (a.out_f32 != nullptr) *reinterpret_cast<float4*>(a.out_f32 + dest * a.ld32 + i * 4) = y;
-    if (a.out_bf16 != nullptr)
-      *reinterpret_cast<uint2*>(a.out_bf16 + dest * a.ld16 + i * 4) = make_uint2(pack_bf16(y.x, y.y), pack_bf16(y.z, y.w));
+    if (a.out_bf16 != nullptr) {
+      if (a.split) store_split4(a.out_bf16 + dest * a.ld16, C, i * 4, y);
+      else *reinterpret_cast<uint2*>(a.out_bf16 + dest * a.ld16 + i * 4) = make_uint2(pack_bf16(y.x, y.y), pack_bf16(y.z, y.w));
+    }
     if (a.out_raw != nullptr) *reinterpret_cast<float4*>(a.out_raw + r * a.ld_raw + i * 4) = v[t];
   }
 }
@@ -180,9 +197,27 @@ __global__ void cast_bf16_kernel(const float* __restrict__ in, int ld_in, __nv_b
   }
 }
 
+// fp32 [M, C] (row pitch ld_in) -> split bf16 [M, 3 * ldp]: [hi (ldp) | lo (ldp) | hi (ldp)], columns >= C zero
+__global__ void split_bf16_kernel(const float* __restrict__ in, int ld_in, __nv_bfloat16* __restrict__ out, int ldp, int M,
+                                  int C) {
+  const long long total = static_cast<long long>(M) * ldp;
+  for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long row = idx / ldp;
+    const int col = static_cast<int>(idx - row * ldp);
+    const float x = col < C ? in[row * ld_in + col] : 0.f;
+    const __nv_bfloat16 hi = __float2bfloat16(x);
+    const __nv_bfloat16 lo = __float2bfloat16(x - __bfloat162float(hi));
+    __nv_bfloat16* o = out + row * (3LL * ldp);
+    o[col] = hi;
+    o[ldp + col] = lo;
+    o[2 * ldp + col] = hi;
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ patch im2col
 __global__ void __launch_bounds__(256) patch_im2col_kernel(const float* __restrict__ frames,
-                                                           __nv_bfloat16* __restrict__ out, int H, int W) {
+                                                           __nv_bfloat16* __restrict__ out, int H, int W, int split) {
   extern __shared__ float s_img[];  // [3][4][W]
   const int PH = H >> 2, PW = W >> 2;
   const int f = blockIdx.x / PH, py = blockIdx.x - f * PH;
@@ -195,14 +230,20 @@ __global__ void __launch_bounds__(256) patch_im2col_kernel(const float* __restri
     *reinterpret_cast<float4*>(s_img + cr * W + x4 * 4) = v;
   }
   __syncthreads();
-  __nv_bfloat16* dst = out + (static_cast<size_t>(f) * PH + py) * PW * 48;
+  const int pitch = split ? 144 : 48;
+  __nv_bfloat16* dst = out + (static_cast<size_t>(f) * PH + py) * PW * pitch;
   for (int idx = threadIdx.x; idx < PW * 6; idx += blockDim.x) {
     const int px = idx / 6, j = idx - px * 6;
     const int c = j >> 1, dy0 = (j & 1) * 2;
     const float* r0 = s_img + (c * 4 + dy0) * W + px * 4;
     const float* r1 = r0 + W;
-    *reinterpret_cast<uint4*>(dst + px * 48 + j * 8) =
-        make_uint4(pack_bf16(r0[0], r0[1]), pack_bf16(r0[2], r0[3]), pack_bf16(r1[0], r1[1]), pack_bf16(r1[2], r1[3]));
+    if (!split) {
+      *reinterpret_cast<uint4*>(dst + px * 48 + j * 8) =
+          make_uint4(pack_bf16(r0[0], r0[1]), pack_bf16(r0[2], r0[3]), pack_bf16(r1[0], r1[1]), pack_bf16(r1[2], r1[3]));
+    } else {   // fp32-grade mode: [hi(48) | lo(48) | hi(48)]
+      store_split4(dst + px * 144, 48, j * 8, make_float4(r0[0], r0[1], r0[2], r0[3]));
+      store_split4(dst + px * 144, 48, j * 8 + 4, make_float4(r1[0], r1[1], r1[2], r1[3]));
+    }
   }
 }
 
@@ -340,7 +381,8 @@ __global__ void __launch_bounds__(256) text_embed_ln_kernel(const int64_t* __res
                                                             const float* __restrict__ pemb, const float* __restrict__ type0,
                                                             int vocab, const float* __restrict__ gamma,
                                                             const float* __restrict__ beta, float eps, int D,
-                                                            float* __restrict__ out_f32, __nv_bfloat16* __restrict__ out_bf16) {
+                                                            float* __restrict__ out_f32, __nv_bfloat16* __restrict__ out_bf16,
+                                                            int split) {
   const int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (r >= rows) return;
@@ -385,9 +427,11 @@ __global__ void __launch_bounds__(256) text_embed_ln_kernel(const int64_t* __res
       y.z = (v[t].z - mean) * rstd * g.z + b.z;
       y.w = (v[t].w - mean) * rstd * g.w + b.w;
       if (out_f32 != nullptr) *reinterpret_cast<float4*>(out_f32 + static_cast<size_t>(r) * D + i * 4) = y;
-      if (out_bf16 != nullptr)
-        *reinterpret_cast<uint2*>(out_bf16 + static_cast<size_t>(r) * D + i * 4) =
+      if (out_bf16 != nullptr) {
+        if (split) store_split4(out_bf16 + static_cast<size_t>(r) * 3 * D, D, i * 4, y);
+        else *reinterpret_cast<uint2*>(out_bf16 + static_cast<size_t>(r) * D + i * 4) =
             make_uint2(pack_bf16(y.x, y.y), pack_bf16(y.z, y.w));
+      }
     }
   }
 }
@@ -452,8 +496,15 @@ __global__ void cmt_embed_kernel(const float* __restrict__ x, int rows_total, in
 }
 
 // ------------------------------------------------------------------------------------------------ pooling + classifier
+__device__ __forceinline__ float2 ld2f(const __nv_bfloat16* p) {
+  const __nv_bfloat162 v = *reinterpret_cast<const __nv_bfloat162*>(p);
+  return make_float2(__bfloat162float(v.x), __bfloat162float(v.y));
+}
+__device__ __forceinline__ float2 ld2f(const float* p) { return *reinterpret_cast<const float2*>(p); }
+
+template <typename TH>
 __global__ void __launch_bounds__(256) pool_classify_kernel(const float* __restrict__ x,
-                                                            const __nv_bfloat16* __restrict__ th,
+                                                            const TH* __restrict__ th,
                                                             const float* __restrict__ mask, const float* __restrict__ wv,
                                                             float bv, const float* __restrict__ wc,
                                                             const float* __restrict__ bc, int L, int H, int labels,
@@ -465,12 +516,12 @@ __global__ void __launch_bounds__(256) pool_classify_kernel(const float* __restr
   const int u = blockIdx.x;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
   for (int t = warp; t < L; t += nwarps) {
-    const __nv_bfloat16* row = th + (static_cast<size_t>(u) * L + t) * H;
+    const TH* row = th + (static_cast<size_t>(u) * L + t) * H;
     float acc = 0.f;
     for (int c = lane * 2; c < H; c += 64) {
-      const __nv_bfloat162 v = *reinterpret_cast<const __nv_bfloat162*>(row + c);
-      acc = fmaf(__bfloat162float(v.x), wv[c], acc);
-      acc = fmaf(__bfloat162float(v.y), wv[c + 1], acc);
+      const float2 v = ld2f(row + c);
+      acc = fmaf(v.x, wv[c], acc);
+      acc = fmaf(v.y, wv[c + 1], acc);
     }
     acc = warp_sum(acc);
     if (lane == 0) s_sc[t] = mask[static_cast<size_t>(u) * L + t] == 0.f ? -INFINITY : acc + bv;
@@ -568,7 +619,7 @@ cudaError_t launch_layernorm(const LnArgs& a, cudaStream_t stream) {
   if ((a.ld_in % 4) != 0 || (a.out_f32 && (a.ld32 % 4) != 0) || (a.out_bf16 && (a.ld16 % 4) != 0))
     return cudaErrorInvalidValue;
   LnParams p{a.in, a.ld_in, a.M, a.nseg, a.cseg, a.map, a.map_period, a.src_period, a.gamma, a.beta, a.eps,
-             a.out_f32, a.ld32, a.out_bf16, a.ld16, a.rows_in, a.rows_out, a.row_off, a.out_raw, a.ld_raw};
+             a.out_f32, a.ld32, a.out_bf16, a.ld16, a.rows_in, a.rows_out, a.row_off, a.out_raw, a.ld_raw, a.split};
   switch (C) {  // specialised row shapes of the path; anything else takes the generic one-row-per-warp kernel
     case 96: return launch_ln_vec<8, 3>(p, stream);
     case 192: return launch_ln_vec<16, 3>(p, stream);
@@ -590,9 +641,16 @@ cudaError_t launch_cast_bf16(const float* in, int ld_in, __nv_bfloat16* out, int
   return cudaGetLastError();
 }
 
-cudaError_t launch_patch_im2col(const float* frames, __nv_bfloat16* out, int F, int H, int W, cudaStream_t stream) {
+cudaError_t launch_split_bf16(const float* in, int ld_in, __nv_bfloat16* out, int ldp, int M, int C, cudaStream_t stream) {
+  if (M <= 0 || C <= 0 || ldp < C) return cudaErrorInvalidValue;
+  split_bf16_kernel<<<grid_for(static_cast<long long>(M) * ldp, 256), 256, 0, stream>>>(in, ld_in, out, ldp, M, C);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_patch_im2col(const float* frames, __nv_bfloat16* out, int F, int H, int W, int split,
+                                cudaStream_t stream) {
   if (F <= 0 || (H % 4) != 0 || (W % 4) != 0 || W > 1024) return cudaErrorInvalidValue;
-  patch_im2col_kernel<<<F * (H / 4), 256, 12 * W * sizeof(float), stream>>>(frames, out, H, W);
+  patch_im2col_kernel<<<F * (H / 4), 256, 12 * W * sizeof(float), stream>>>(frames, out, H, W, split);
   return cudaGetLastError();
 }
 
@@ -628,12 +686,12 @@ cudaError_t launch_filter_pack(const float* vision, const float* vision_mask, co
 cudaError_t launch_text_embed(const int64_t* ids, int* pos_scratch, int U, int L, int kind_roberta, int pad_id,
                               const float* word, const float* pos, const float* type0, int max_pos, int vocab,
                               const float* gamma, const float* beta, float eps, int D, float* out_f32,
-                              __nv_bfloat16* out_bf16, cudaStream_t stream) {
+                              __nv_bfloat16* out_bf16, int split, cudaStream_t stream) {
   if (U <= 0 || L <= 0 || (D % 4) != 0 || D > LN_NV * 128) return cudaErrorInvalidValue;
   text_posids_kernel<<<U, 32, 0, stream>>>(ids, L, kind_roberta, pad_id, max_pos, pos_scratch);
   const int rows = U * L;
   text_embed_ln_kernel<<<(rows + 7) / 8, 256, 0, stream>>>(ids, pos_scratch, rows, word, pos, type0, vocab, gamma, beta,
-                                                          eps, D, out_f32, out_bf16);
+                                                          eps, D, out_f32, out_bf16, split);
   return cudaGetLastError();
 }
 
@@ -652,13 +710,14 @@ cudaError_t launch_cmt_embed(const float* x, int rows_in, int rows_total, int ro
   return cudaGetLastError();
 }
 
-cudaError_t launch_pool_classify(const float* x, const __nv_bfloat16* th, const float* mask, const float* wv, float bv,
-                                 const float* wc, const float* bc, int U, int L, int H, int labels, float* logits,
-                                 cudaStream_t stream) {
-  if (U <= 0 || L <= 0 || (H % 64) != 0) return cudaErrorInvalidValue;
+cudaError_t launch_pool_classify(const float* x, const __nv_bfloat16* th, const float* th_f32, const float* mask,
+                                 const float* wv, float bv, const float* wc, const float* bc, int U, int L, int H,
+                                 int labels, float* logits, cudaStream_t stream) {
+  if (U <= 0 || L <= 0 || (H % 64) != 0 || ((th == nullptr) == (th_f32 == nullptr))) return cudaErrorInvalidValue;
   const size_t smem = (L + H) * sizeof(float);
   if (smem > 48 * 1024) return cudaErrorInvalidValue;
-  pool_classify_kernel<<<U, 256, smem, stream>>>(x, th, mask, wv, bv, wc, bc, L, H, labels, logits);
+  if (th != nullptr) pool_classify_kernel<__nv_bfloat16><<<U, 256, smem, stream>>>(x, th, mask, wv, bv, wc, bc, L, H, labels, logits);
+  else pool_classify_kernel<float><<<U, 256, smem, stream>>>(x, th_f32, mask, wv, bv, wc, bc, L, H, labels, logits);
   return cudaGetLastError();
 }
 

@@ -10,6 +10,13 @@ namespace fmmt {
 cudaError_t launch_window_attention(const __nv_bfloat16* qkv, __nv_bfloat16* out, const float* bias,
                                     const int8_t* rid, int num_windows, int nW, int heads, int C, int N, float scale,
                                     cudaStream_t stream);
+// fp32-grade mode variants (SIMT fp32 math): fp32 inputs; the output is the split-bf16 operand [hi | lo | hi] of the next
+// Linear (row pitch ldo = 3 * width)
+cudaError_t launch_window_attention_f32(const float* qkv, __nv_bfloat16* out_split, const float* bias, const int8_t* rid,
+                                        int num_windows, int nW, int heads, int C, int N, float scale, cudaStream_t stream);
+cudaError_t launch_mha_f32(const float* q, int ldq, const float* k, int ldk, const float* v, int ldv,
+                           __nv_bfloat16* out_split, int width, const float* key_mask, float mask_neg, int B, int H, int Lq,
+                           int Lk, float scale, cudaStream_t stream);
 cudaError_t launch_mha(const __nv_bfloat16* q, int ldq, const __nv_bfloat16* k, int ldk, const __nv_bfloat16* v,
                        int ldv, __nv_bfloat16* out, int ldo, const float* key_mask, float mask_neg, int B, int H,
                        int Lq, int Lk, float scale, cudaStream_t stream);
@@ -39,6 +46,7 @@ struct LnArgs {
   int rows_in = 0, rows_out = 0, row_off = 0;
   float* out_raw = nullptr;  // optional fp32 copy of the (gathered) un-normalised input rows, row r -> out_raw[r]
   int ld_raw = 0;
+  int split = 0;             // fp32-grade mode: out_bf16 rows are [hi | lo | hi] (3C wide; ld16 >= 3C)
 };
 cudaError_t launch_layernorm(const LnArgs& a, cudaStream_t stream);
 
@@ -46,8 +54,13 @@ cudaError_t launch_layernorm(const LnArgs& a, cudaStream_t stream);
 cudaError_t launch_cast_bf16(const float* in, int ld_in, __nv_bfloat16* out, int ld_out, int M, int C,
                              cudaStream_t stream);
 
+// fp32-grade mode: fp32 [M, C] -> split bf16 [M, 3*ldp] = [hi | lo | hi] (each ldp wide, zero padded past C)
+cudaError_t launch_split_bf16(const float* in, int ld_in, __nv_bfloat16* out, int ldp, int M, int C, cudaStream_t stream);
+
 // PatchEmbed im2col: frames fp32 (F,3,H,W) -> bf16 [F*(H/4)*(W/4), 48], k = c*16 + dy*4 + dx (Swin_Transformer.py:419)
-cudaError_t launch_patch_im2col(const float* frames, __nv_bfloat16* out, int F, int H, int W, cudaStream_t stream);
+//   split = 1 (fp32-grade mode): rows are [hi(48) | lo(48) | hi(48)]
+cudaError_t launch_patch_im2col(const float* frames, __nv_bfloat16* out, int F, int H, int W, int split,
+                                cudaStream_t stream);
 
 // Swin-cls tail: feat512 -> Linear(512,64) -> ReLU -> Linear(64,7) [-> softmax((z+g)/tau), sum p^2]
 //   (src/models.py:28-32, train.py:183-184). w1t is [feat, hidden] (transposed), w2 is [labels, hidden].
@@ -64,7 +77,7 @@ cudaError_t launch_filter_pack(const float* vision, const float* vision_mask, co
 cudaError_t launch_text_embed(const int64_t* ids, int* pos_scratch, int U, int L, int kind_roberta, int pad_id,
                               const float* word, const float* pos, const float* type0, int max_pos, int vocab,
                               const float* gamma, const float* beta, float eps, int D, float* out_f32,
-                              __nv_bfloat16* out_bf16, cudaStream_t stream);
+                              __nv_bfloat16* out_bf16, int split, cudaStream_t stream);
 
 // Utterance span extraction (src/models.py:112-150): text [U,L,H] -> out [U,max_len,H] (+0/1 mask)
 cudaError_t launch_span_extract(const float* text, const int64_t* sep_mask, const int64_t* idx_in_dia, int U, int L,
@@ -76,9 +89,10 @@ cudaError_t launch_cmt_embed(const float* x, int rows_in, int rows_total, int ro
 
 // AdditiveAttention tail + classifier (modules/Transformer.py:34-43; src/models.py:186-187):
 //   score_t = wv . th[t] + bv (th = tanh(P x + Q q) from the GEMM), mask -> -inf, softmax, y = sum a_t x_t, logits = Wc y + bc
-cudaError_t launch_pool_classify(const float* x, const __nv_bfloat16* th, const float* mask, const float* wv, float bv,
-                                 const float* wc, const float* bc, int U, int L, int H, int labels, float* logits,
-                                 cudaStream_t stream);
+//   th (bf16) or th_f32 (fp32-grade mode): exactly one of the two
+cudaError_t launch_pool_classify(const float* x, const __nv_bfloat16* th, const float* th_f32, const float* mask,
+                                 const float* wv, float bv, const float* wc, const float* bc, int U, int L, int H,
+                                 int labels, float* logits, cudaStream_t stream);
 
 // out[q*period + t] = in[q*period + map[t]] for rows of C floats (parity captures of permuted activations)
 cudaError_t launch_gather_rows(const float* in, const int* map, int period, int C, int M, float* out,

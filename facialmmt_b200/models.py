@@ -28,8 +28,18 @@ def _require_cuda():
         raise _lib.FmmtError("facialmmt_b200 needs a CUDA (sm_100a) device: there is no CPU fallback")
 
 
-def _cfg_c(cfg: FmmtConfig, model: int, swin_chunk: int = 0, swin_chunk_late: int = 0) -> _lib.FmmtConfigC:
+def _precision_code(precision: str) -> int:
+    if precision in ("bf16", None):
+        return _lib.PRECISION_BF16
+    if precision in ("fp32", "f32", "float32"):
+        return _lib.PRECISION_FP32
+    raise ValueError(f"precision must be 'bf16' or 'fp32', got {precision!r}")
+
+
+def _cfg_c(cfg: FmmtConfig, model: int, swin_chunk: int = 0, swin_chunk_late: int = 0,
+           precision: str = "bf16") -> _lib.FmmtConfigC:
     c = _lib.FmmtConfigC()
+    c.precision = _precision_code(precision)
     s, t, f = cfg.swin, cfg.text, cfg.fusion
     c.model = model
     c.img_size, c.patch_size, c.in_chans, c.embed_dim = s.img_size, s.patch_size, s.in_chans, s.embed_dim
@@ -61,10 +71,11 @@ class _Module:
 
     _model_kind = 0
 
-    def __init__(self, cfg: FmmtConfig, swin_chunk: int = 0, swin_chunk_late: int = 0):
+    def __init__(self, cfg: FmmtConfig, swin_chunk: int = 0, swin_chunk_late: int = 0, precision: str = "bf16"):
         self.cfg = cfg
+        self.precision = "fp32" if _precision_code(precision) == _lib.PRECISION_FP32 else "bf16"
         self._lib = _lib.load()
-        self._cfg_c = _cfg_c(cfg, self._model_kind, swin_chunk, swin_chunk_late)
+        self._cfg_c = _cfg_c(cfg, self._model_kind, swin_chunk, swin_chunk_late, precision)
         self._h = c_void_p()
         _lib.check(self._lib.fmmt_create(ctypes.byref(self._cfg_c), ctypes.byref(self._h)), "fmmt_create")
         self._finalized = False
@@ -197,7 +208,8 @@ class SwinForAffwildClassification(_Module):
 
     _model_kind = _lib.MODEL_SWIN_CLS
 
-    def __init__(self, args=None, swin_chunk: int = 0, swin_chunk_late: int = 0):
+    def __init__(self, args=None, swin_chunk: int = 0, swin_chunk_late: int = 0, precision: str = None):
+        precision = precision or getattr(args, "precision", "bf16")
         if isinstance(args, FmmtConfig):
             cfg = args
             self.tau = cfg.tau
@@ -205,7 +217,7 @@ class SwinForAffwildClassification(_Module):
             cfg = FmmtConfig(swin=_swin_config_from_args(args) if args is not None else SwinConfig())
             self.tau = float(getattr(args, "tau", 1.0)) if args is not None else 1.0
         self.num_labels = cfg.swin.num_labels
-        super().__init__(cfg, swin_chunk, swin_chunk_late)
+        super().__init__(cfg, swin_chunk, swin_chunk_late, precision)
 
     def _spec(self):
         return _syn.swin_cls_state_dict_spec(self.cfg.swin)
@@ -271,12 +283,12 @@ class MultiModalTransformerForClassification(_Module):
 
     _model_kind = _lib.MODEL_MULTIMODAL
 
-    def __init__(self, config, text_layers: Optional[int] = None):
+    def __init__(self, config, text_layers: Optional[int] = None, precision: str = None):
         cfg = _fmmt_config_from_namespace(config, text_layers)
         self.choice_modality = getattr(config, "choice_modality", "T+A+V")
         self.num_labels = cfg.fusion.num_labels
         self.text_pretrained_model = cfg.text.kind
-        super().__init__(cfg)
+        super().__init__(cfg, precision=precision or getattr(config, "precision", "bf16"))
 
     def _spec(self):
         return _syn.multimodal_state_dict_spec(self.cfg)
@@ -315,9 +327,9 @@ class meld_utt_transformer(_Module):  # noqa: N801  (reference class name)
 
     _model_kind = _lib.MODEL_UNIMODAL
 
-    def __init__(self, args):
+    def __init__(self, args, precision: str = None):
         cfg = _fmmt_config_from_namespace(args)
-        super().__init__(cfg)
+        super().__init__(cfg, precision=precision or getattr(args, "precision", "bf16"))
 
     def _spec(self):
         return _syn.unimodal_state_dict_spec(self.cfg.fusion)

@@ -45,6 +45,15 @@ extern "C" {
 #define FMMT_TEXT_ROBERTA 0
 #define FMMT_TEXT_BERT 1
 
+/* Arithmetic mode of a handle (north_star: logits within 1e-2 of the fp32 reference in bf16 mode, 1e-3 in fp32 mode).
+ * BF16: bf16 operands, fp32 accumulate, fp32 residual streams / LayerNorm / softmax (the speed build).
+ * FP32: fp32-grade: every Linear runs on the same tcgen05 kernels with split-bf16 x3 operands (A = A_hi + A_lo,
+ *       W = W_hi + W_lo; A_hi W_hi + A_lo W_hi + A_hi W_lo, 16 mantissa bits per operand, fp32 accumulate), attention
+ *       cores and all element-wise math in fp32. About 4x slower; the reference's own arithmetic is fp32
+ *       (src/models.py:95-188). */
+#define FMMT_PRECISION_BF16 0
+#define FMMT_PRECISION_FP32 1
+
 typedef struct fmmt_handle fmmt_handle;
 
 /* Dimensions only (mirrors swin_conf.yaml, main.py:62-83 and the HF roberta-large / bert-large configs). */
@@ -65,6 +74,7 @@ typedef struct fmmt_config {
   int32_t cmt_layers_ta, cmt_heads_ta, cmt_layers_tav, cmt_heads_tav;
   int32_t text_len, audio_len, vision_len;
   float eps;
+  int32_t precision; /* FMMT_PRECISION_* */
 } fmmt_config;
 
 FMMT_API const char* fmmt_last_error(void);
