@@ -52,6 +52,9 @@ SIGNATURES = {
     "fmmt_finalize": (c_int, [c_void_p]),
     "fmmt_swin_forward": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_float, c_void_p, c_void_p, c_void_p,
                                   c_void_p, c_void_p]),
+    "fmmt_swin_forward_u8": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_float, c_void_p, c_void_p, c_void_p,
+                                     c_void_p, c_void_p]),
+    "fmmt_op_frame_ingest": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
     "fmmt_filter_pack": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_float, c_int, c_void_p, c_void_p,
                                  c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "fmmt_multimodal_forward": (c_int, [c_void_p] * 9 + [c_int, c_int, c_void_p, c_void_p]),
@@ -61,6 +64,8 @@ SIGNATURES = {
     "fmmt_set_profile": (c_int, [c_void_p, c_int]),
     "fmmt_profile_read": (c_int64, [c_void_p, c_void_p, c_int64]),
     "fmmt_debug_timeout": (ctypes.c_uint32, [c_int]),
+    "fmmt_debug_umma": (c_int, [c_void_p, c_int, c_void_p, c_int, ctypes.c_uint64, ctypes.c_uint64, ctypes.c_uint32,
+                                ctypes.c_uint32, ctypes.c_uint32, c_int, c_int, c_int, c_int, c_void_p]),
     "fmmt_debug_mma_cycles": (c_double, [c_int, c_int]),
     "fmmt_debug_feed": (c_int, [c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "fmmt_debug_feed2": (c_double, [c_int, c_int, c_int, c_int, c_int, c_int]),

@@ -17,7 +17,8 @@ CSRC = PKG_DIR / "csrc"
 BUILD_DIR = CSRC / "build"
 LIB_PATH = PKG_DIR / "libfacialmmt_b200.so"
 
-SOURCES = ["gemm.cu", "mlp_fused.cu", "mlp_stream.cu", "kernels.cu", "attention.cu", "engine.cu", "capi.cu"]
+SOURCES = ["gemm.cu", "mlp_fused.cu", "mlp_stream.cu", "kernels.cu", "attention.cu", "attn_fused.cu", "ingest.cu",
+           "umma_probe.cu", "engine.cu", "capi.cu"]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
@@ -25,6 +26,7 @@ NVCC_FLAGS = [
     "-DFMMT_BUILD",
     "-Xcompiler", "-fPIC",
     "-Xcompiler", "-fvisibility=hidden",
+    "-Xcompiler", "-ffp-contract=off",     # ingest.cu builds OpenCV's tap tables on the host: no FMA contraction there
     "-cudart", "static",
 ]
 

@@ -19,6 +19,12 @@ static int check_cuda(cudaError_t e, const char* what) {
 }
 }  // namespace fmmt
 
+namespace fmmt {
+int umma_probe(const void* a_img, int a_bytes, const void* b_img, int b_bytes, unsigned long long adesc_tpl,
+               unsigned long long bdesc_tpl, unsigned int a_off, unsigned int b_off, unsigned int idesc, int ksteps,
+               int a_step, int b_step, int ncols, float* out);
+}
+
 using namespace fmmt;
 
 struct fmmt_handle {
@@ -68,6 +74,19 @@ FMMT_API int fmmt_swin_forward(fmmt_handle* h, const float* frames, int n_frames
                                float* logits, float* probs, float* importance, float* feat, void* stream) {
   if (!h) return set_error(FMMT_ERR_INVALID, "null handle");
   return h->eng->swin_forward(frames, n_frames, gumbel, tau, logits, probs, importance, feat, S(stream));
+}
+
+FMMT_API int fmmt_swin_forward_u8(fmmt_handle* h, const uint8_t* crops, int n_frames, int crop_h, int crop_w,
+                                  const float* gumbel, float tau, float* logits, float* probs, float* importance, float* feat,
+                                  void* stream) {
+  if (!h) return set_error(FMMT_ERR_INVALID, "null handle");
+  return h->eng->swin_forward_u8(crops, n_frames, crop_h, crop_w, gumbel, tau, logits, probs, importance, feat, S(stream));
+}
+
+FMMT_API int fmmt_op_frame_ingest(const uint8_t* crops, int n_frames, int crop_h, int crop_w, float* out_f32, void* stream) {
+  if (!crops || !out_f32) return set_error(FMMT_ERR_INVALID, "fmmt_op_frame_ingest: null pointer");
+  count_launch();
+  return check_cuda(launch_frame_ingest(crops, n_frames, crop_h, crop_w, out_f32, nullptr, 0, S(stream)), "fmmt_op_frame_ingest");
 }
 
 FMMT_API int fmmt_filter_pack(const float* vision, const float* vision_mask, const int32_t* frame_off, int total_frames,
@@ -127,6 +146,16 @@ FMMT_API uint32_t fmmt_debug_timeout(int reset) {
   const uint32_t b = read_mlp_timeout(reset != 0);
   const uint32_t c = read_mlp_stream_timeout(reset != 0);
   return a != 0 ? a : (b != 0 ? b : c);
+}
+
+FMMT_API int fmmt_debug_umma(const void* a_img, int a_bytes, const void* b_img, int b_bytes, uint64_t adesc_tpl,
+                             uint64_t bdesc_tpl, uint32_t a_off, uint32_t b_off, uint32_t idesc, int ksteps, int a_step,
+                             int b_step, int ncols, float* out) {
+  if (!a_img || !b_img || !out) return set_error(FMMT_ERR_INVALID, "fmmt_debug_umma: null pointer");
+  const int rc = umma_probe(a_img, a_bytes, b_img, b_bytes, adesc_tpl, bdesc_tpl, a_off, b_off, idesc, ksteps, a_step, b_step,
+                            ncols, out);
+  if (rc != 0) return set_error(rc == -3 ? FMMT_ERR_CUDA : FMMT_ERR_INVALID, "fmmt_debug_umma failed");
+  return FMMT_OK;
 }
 
 FMMT_API double fmmt_debug_mma_cycles(int n, int iters) { return mma_rate_probe(n & 0xFFFF, iters, n >> 16); }

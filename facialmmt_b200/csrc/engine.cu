@@ -839,7 +839,7 @@ void Engine::swin_block(const SwinStageW& sw, const SwinBlockW& bw, float*& x, f
 
 static int swin_split(const fmmt_config& c) { return c.num_stages >= 3 ? 2 : (c.num_stages - 1); }
 
-void Engine::swin_early(const float* frames, int f0, int nf, float* x_out) {
+void Engine::swin_early(const FrameSrc& frames, int f0, int nf, float* x_out) {
   const fmmt_config& c = cfg_;
   const int split = swin_split(c);
   const SwinStageW& s0 = swin_.stages[0];
@@ -853,7 +853,11 @@ void Engine::swin_early(const float* frames, int f0, int nf, float* x_out) {
   bf16* a = arena_.alloc<bf16>(static_cast<size_t>(M) * C0 * kw_);
   bf16* hid = arena_.alloc<bf16>(static_cast<size_t>(M) * c.mlp_ratio * C0 * kw_);
   const size_t frame_elems = static_cast<size_t>(3) * c.img_size * c.img_size;
-  OP(launch_patch_im2col(frames + static_cast<size_t>(f0) * frame_elems, col, nf, c.img_size, c.img_size, precise_, st_), "im2col");
+  if (frames.u8 != nullptr)     // resize + normalise + unfold in one pass over the uint8 crops (utils/dataset.py:47-69)
+    OP(launch_frame_ingest(frames.u8 + static_cast<size_t>(f0) * frames.h * frames.w * 3, nf, frames.h, frames.w, nullptr, col,
+                           precise_, st_), "frame_ingest");
+  else
+    OP(launch_patch_im2col(frames.f32 + static_cast<size_t>(f0) * frame_elems, col, nf, c.img_size, c.img_size, precise_, st_), "im2col");
   GemmArgs g;
   g.out_f32 = x; g.ldo32 = C0;
   gemm_lin(col, 48, M, swin_.patch, g);                              // Conv2d(3,96,k4,s4) as GEMM (K = 48)
@@ -922,7 +926,7 @@ void Engine::swin_late(float* x, int f0, int nf, bf16* feat_ln) {
   ln(lf);
 }
 
-void Engine::swin_body(const float* frames, int F, const float* gumbel, float tau, float* logits, float* probs,
+void Engine::swin_body(const FrameSrc& frames, int F, const float* gumbel, float tau, float* logits, float* probs,
                        float* importance, float* feat) {
   const fmmt_config& c = cfg_;
   const int split = swin_split(c);
@@ -967,7 +971,22 @@ int Engine::swin_forward(const float* frames, int F, const float* gumbel, float 
   if (cfg_.model != FMMT_MODEL_SWIN_CLS) return set_error(FMMT_ERR_STATE, "handle is not a Swin-cls model");
   if (!frames || F <= 0) return set_error(FMMT_ERR_INVALID, "fmmt_swin_forward: frames/n_frames");
   if (tau == 0.f) return set_error(FMMT_ERR_INVALID, "fmmt_swin_forward: tau must be non-zero");
-  return run([&] { swin_body(frames, F, gumbel, tau, logits, probs, importance, feat); }, st);
+  FrameSrc src;
+  src.f32 = frames;
+  return run([&] { swin_body(src, F, gumbel, tau, logits, probs, importance, feat); }, st);
+}
+
+int Engine::swin_forward_u8(const uint8_t* crops, int F, int crop_h, int crop_w, const float* gumbel, float tau,
+                            float* logits, float* probs, float* importance, float* feat, cudaStream_t st) {
+  if (cfg_.model != FMMT_MODEL_SWIN_CLS) return set_error(FMMT_ERR_STATE, "handle is not a Swin-cls model");
+  if (!crops || F <= 0 || crop_h <= 0 || crop_w <= 0) return set_error(FMMT_ERR_INVALID, "fmmt_swin_forward_u8: crops/n_frames/size");
+  if (tau == 0.f) return set_error(FMMT_ERR_INVALID, "fmmt_swin_forward_u8: tau must be non-zero");
+  if (cfg_.img_size != 224) return set_error(FMMT_ERR_INVALID, "fmmt_swin_forward_u8: the ingest resizes to 224 (utils/dataset.py:20)");
+  if (crop_h == 224 && crop_w != 224)
+    return set_error(FMMT_ERR_INVALID, "fmmt_swin_forward_u8: a crop of height 224 is not resized and must be 224 wide");
+  FrameSrc src;
+  src.u8 = crops; src.h = crop_h; src.w = crop_w;
+  return run([&] { swin_body(src, F, gumbel, tau, logits, probs, importance, feat); }, st);
 }
 
 // =================================================================================================== fusion forward

@@ -144,6 +144,8 @@ class Engine {
   int finalize();
   int swin_forward(const float* frames, int F, const float* gumbel, float tau, float* logits, float* probs,
                    float* importance, float* feat, cudaStream_t st);
+  int swin_forward_u8(const uint8_t* crops, int F, int crop_h, int crop_w, const float* gumbel, float tau, float* logits,
+                      float* probs, float* importance, float* feat, cudaStream_t st);
   int multimodal_forward(const int64_t* ids, const int64_t* mask, const int64_t* sep, const float* audio,
                          const float* audio_mask, const float* vision, const float* vision_mask, const int64_t* idx,
                          int U, int L, float* logits, cudaStream_t st);
@@ -198,9 +200,11 @@ class Engine {
   void capture(const std::string& name, const float* src, size_t count, size_t dst_off = 0);
 
   // ---- forward bodies (run twice the first time a size is seen: dry sizing pass, then real)
-  void swin_body(const float* frames, int F, const float* gumbel, float tau, float* logits, float* probs,
+  // frames: fp32 (F,3,img,img) as the reference DataLoader yields them, or uint8 crops (F,h,w,3) ingested on the device
+  struct FrameSrc { const float* f32 = nullptr; const uint8_t* u8 = nullptr; int h = 0, w = 0; };
+  void swin_body(const FrameSrc& frames, int F, const float* gumbel, float tau, float* logits, float* probs,
                  float* importance, float* feat);
-  void swin_early(const float* frames, int f0, int nf, float* x2_out);
+  void swin_early(const FrameSrc& frames, int f0, int nf, float* x2_out);
   void swin_late(float* x2, int f0, int nf, bf16* feat_ln);
   void swin_block(const SwinStageW& sw, const SwinBlockW& bw, float*& x, float*& xalt, int nf, bf16* h, void* qkv,
                   bf16* a, bf16* hid);

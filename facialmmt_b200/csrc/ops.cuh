@@ -62,6 +62,13 @@ cudaError_t launch_split_bf16(const float* in, int ld_in, __nv_bfloat16* out, in
 cudaError_t launch_patch_im2col(const float* frames, __nv_bfloat16* out, int F, int H, int W, int split,
                                 cudaStream_t stream);
 
+// ---- ingest.cu
+// Frame ingest (utils/dataset.py:47-69): uint8 crops (F, H, W, 3) as cv2.imread yields them -> cv2-exact INTER_CUBIC (H < 224)
+// / INTER_AREA (H > 224) resize to 224 x 224 -> (v/255 - 0.5)/0.5 -> out_f32 (F,3,224,224) fp32 and / or the PatchEmbed im2col
+// rows out_col bf16 [F*3136, 48] (split = 1: [hi|lo|hi], 144 wide). cudaErrorInvalidValue for sizes the reference rejects.
+cudaError_t launch_frame_ingest(const uint8_t* crops, int F, int H, int W, float* out_f32, __nv_bfloat16* out_col, int split,
+                                cudaStream_t stream);
+
 // Swin-cls tail: feat512 -> Linear(512,64) -> ReLU -> Linear(64,7) [-> softmax((z+g)/tau), sum p^2]
 //   (src/models.py:28-32, train.py:183-184). w1t is [feat, hidden] (transposed), w2 is [labels, hidden].
 cudaError_t launch_swin_tail(const float* feat, int feat_dim, const float* w1t, const float* b1, int hidden,

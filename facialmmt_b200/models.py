@@ -228,11 +228,19 @@ class SwinForAffwildClassification(_Module):
         if not self._finalized:
             raise _lib.FmmtError("load_state_dict() must be called before forward()")
         s = self.cfg.swin
-        x = _f32(images_feature)
-        if x.dim() != 4 or tuple(x.shape[1:]) != (s.in_chans, s.img_size, s.img_size):
-            # PatchEmbed asserts the input size (Swin_Transformer.py:417-418)
-            raise ValueError(f"Input image size {tuple(x.shape)} doesn't match model "
-                             f"(*,{s.in_chans},{s.img_size},{s.img_size}).")
+        u8 = images_feature.dtype == torch.uint8
+        if u8:
+            # decoded crops (F, h, w, 3) uint8 as cv2.imread yields them: resized + normalised on the device
+            # (utils/dataset.py:47-69), see fmmt_swin_forward_u8
+            x = images_feature.to(device="cuda", non_blocking=True).contiguous()
+            if x.dim() != 4 or x.shape[3] != 3:
+                raise ValueError(f"uint8 crops must be (F, h, w, 3), got {tuple(x.shape)}")
+        else:
+            x = _f32(images_feature)
+            if x.dim() != 4 or tuple(x.shape[1:]) != (s.in_chans, s.img_size, s.img_size):
+                # PatchEmbed asserts the input size (Swin_Transformer.py:417-418)
+                raise ValueError(f"Input image size {tuple(x.shape)} doesn't match model "
+                                 f"(*,{s.in_chans},{s.img_size},{s.img_size}).")
         F = x.shape[0]
         g = _f32(gumbel) if gumbel is not None else None
         if g is not None and tuple(g.shape) != (F, s.num_labels):
@@ -241,9 +249,14 @@ class SwinForAffwildClassification(_Module):
         probs = torch.empty_like(logits)
         imp = torch.empty(F, device="cuda", dtype=torch.float32)
         feat = torch.empty(F, s.feat_dim, device="cuda", dtype=torch.float32) if want_feat else None
-        _lib.check(self._lib.fmmt_swin_forward(self._h, _lib.ptr(x), F, _lib.ptr(g), float(self.tau), _lib.ptr(logits),
-                                               _lib.ptr(probs), _lib.ptr(imp), _lib.ptr(feat), _lib.cur_stream()),
-                   "fmmt_swin_forward")
+        if u8:
+            _lib.check(self._lib.fmmt_swin_forward_u8(self._h, _lib.ptr(x), F, int(x.shape[1]), int(x.shape[2]), _lib.ptr(g),
+                                                      float(self.tau), _lib.ptr(logits), _lib.ptr(probs), _lib.ptr(imp),
+                                                      _lib.ptr(feat), _lib.cur_stream()), "fmmt_swin_forward_u8")
+        else:
+            _lib.check(self._lib.fmmt_swin_forward(self._h, _lib.ptr(x), F, _lib.ptr(g), float(self.tau), _lib.ptr(logits),
+                                                   _lib.ptr(probs), _lib.ptr(imp), _lib.ptr(feat), _lib.cur_stream()),
+                       "fmmt_swin_forward")
         return (logits, probs, imp, feat) if want_feat else (logits, probs, imp)
 
     def forward(self, images_feature=None, is_trg_task=None, labels=None, criterion=None, gumbel=None):
@@ -347,6 +360,21 @@ class meld_utt_transformer(_Module):  # noqa: N801  (reference class name)
         _lib.check(self._lib.fmmt_unimodal_forward(self._h, _lib.ptr(x), _lib.ptr(m), U, _lib.ptr(logits),
                                                    _lib.cur_stream()), "fmmt_unimodal_forward")
         return logits
+
+
+def frame_ingest(crops_u8: torch.Tensor) -> torch.Tensor:
+    """utils/dataset.py:47-69 on the device: uint8 crops (F, h, w, 3) (cv2.imread bytes) -> fp32 (F, 3, 224, 224), bit-exact
+    with the reference's cv2 (non-IPP) resize + ToTensor + Normalize. The model forwards fuse this step (pass the uint8
+    crops straight to SwinForAffwildClassification); this entry exists for parity tests and for callers that want the tensor."""
+    _require_cuda()
+    lib = _lib.load()
+    x = crops_u8.to(device="cuda").contiguous()
+    if x.dtype != torch.uint8 or x.dim() != 4 or x.shape[3] != 3:
+        raise ValueError("crops must be uint8 (F, h, w, 3)")
+    out = torch.empty(x.shape[0], 3, 224, 224, device="cuda", dtype=torch.float32)
+    _lib.check(lib.fmmt_op_frame_ingest(_lib.ptr(x), int(x.shape[0]), int(x.shape[1]), int(x.shape[2]), _lib.ptr(out),
+                                        _lib.cur_stream()), "fmmt_op_frame_ingest")
+    return out
 
 
 def filter_pack(vision_inputs: torch.Tensor, vision_mask: torch.Tensor, num_imgs, probs: torch.Tensor,

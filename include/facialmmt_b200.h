@@ -103,6 +103,16 @@ FMMT_API int fmmt_finalize(fmmt_handle* h);
 FMMT_API int fmmt_swin_forward(fmmt_handle* h, const float* frames, int n_frames, const float* gumbel, float tau,
                                float* logits, float* probs, float* importance, float* feat, void* stream);
 
+/* Same forward fed with DECODED uint8 face crops instead of the fp32 tensor: crops (F, crop_h, crop_w, 3) uint8 on the device,
+ * exactly the bytes cv2.imread returns (B,G,R). Replaces utils/dataset.py:47-69 from_image_to_embedding_no_IncepRes + the
+ * host->device copy of its 602 KB/frame fp32 result: cv2.resize to 224x224 (INTER_CUBIC if crop_h < 224, INTER_AREA if
+ * crop_h > 224; decided on the height only, like the reference), ToTensor, Normalize(0.5, 0.5), bit-exact with OpenCV's own
+ * (non-IPP) arithmetic, fused with PatchEmbed's unfold. All crops of one call share one size (group ragged crops by size).
+ * FMMT_ERR_INVALID for sizes the reference itself fails on (crop_h == 224 with crop_w != 224) or > 10x area shrinks. */
+FMMT_API int fmmt_swin_forward_u8(fmmt_handle* h, const uint8_t* crops, int n_frames, int crop_h, int crop_w,
+                                  const float* gumbel, float tau, float* logits, float* probs, float* importance, float* feat,
+                                  void* stream);
+
 /* Frame filter + compaction of the eval glue (train.py:185-232). frame_off: device int32 [U+1], prefix sums of the
  * per-utterance frame counts into `probs` (total_frames rows). per_utterance=1: each utterance decides the
  * "no frame passes" fallback on its own (== the reference at its batch size 1); 0: literal whole-batch decision.
@@ -144,6 +154,14 @@ FMMT_API int64_t fmmt_profile_read(fmmt_handle* h, char* buf, int64_t buf_len);
  * wait inside a kernel timed out since the last reset. Bit 31 set, bits 24-30 barrier id, 12-23 CTA, 0-11 thread.
  * Synchronises the device. Model-level forwards report through fmmt_check instead. */
 FMMT_API uint32_t fmmt_debug_timeout(int reset);
+/* Layout probe (tests): one accumulator group D[128 x ncols] = sum_k A_k B_k on tcgen05 with caller-built shared-memory
+ * operand images (device pointers; copied to 1024-byte aligned shared memory) and descriptor templates (all descriptor
+ * fields except the start address); a_off/b_off: start offsets inside the images; a_step/b_step: descriptor address
+ * increments (16-byte units) per k-step; idesc: instruction descriptor. out: device fp32 [128, ncols]. Synchronous.
+ * Pins the operand layouts of the fused attention kernel (tests/test_umma_layouts_gpu.py). */
+FMMT_API int fmmt_debug_umma(const void* a_img, int a_bytes, const void* b_img, int b_bytes, uint64_t adesc_tpl,
+                             uint64_t bdesc_tpl, uint32_t a_off, uint32_t b_off, uint32_t idesc, int ksteps, int a_step,
+                             int b_step, int ncols, float* out);
 /* Bench probe: cycles per tcgen05.mma (M=128, N=n, K=16, bf16) issued back to back on resident shared-memory tiles, all
  * SMs at once (the tensor-pipe floor the GEMM roofline fractions are read against). Bits 16.. of n select a variant:
  * 1 = tcgen05.commit after every 4 MMAs, 2 = tcgen05.fence before every 4, 4 = alternate two operand tile sets. Synchronous. */
@@ -199,6 +217,10 @@ FMMT_API int fmmt_op_swin_mlp_stream(float* x, int M, int C, const float* gamma,
  * q rows (b*Lq+i), k/v rows (b*Lk+j), head h at columns [64h, 64h+64). key_mask fp32 (B,Lk) of 0/1 or NULL. */
 FMMT_API int fmmt_op_mha(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv, void* out, int ldo,
                          const float* key_mask, float mask_neg, int B, int H, int Lq, int Lk, float scale, void* stream);
+
+/* The frame ingest alone (parity tests): crops uint8 (F, crop_h, crop_w, 3) -> out fp32 (F, 3, 224, 224) as the reference's
+ * DataLoader yields it (utils/dataset.py:47-69). */
+FMMT_API int fmmt_op_frame_ingest(const uint8_t* crops, int n_frames, int crop_h, int crop_w, float* out_f32, void* stream);
 
 /* Target-utterance span extraction (src/models.py:112-150): text fp32 (U,L,H), sep_mask int64 (U,L), idx_in_dia int64 (U)
  * -> out fp32 (U,max_len,H) zero-filled past the span, out_mask fp32 (U,max_len) of 0/1. text_kind FMMT_TEXT_ROBERTA: the

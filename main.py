@@ -46,16 +46,25 @@ def build_parser():
     p.add_argument("--text_len", type=int, default=128)
     p.add_argument("--text_layers", type=int, default=24)
     p.add_argument("--per_utterance", type=int, default=1)
+    p.add_argument("--precision", type=str, default="bf16", choices=["bf16", "fp32"],
+                   help="bf16: bf16 operands / fp32 accumulate (logits within 1e-2 of the fp32 reference); fp32: split-bf16 x3 "
+                        "operands + fp32 attention (within 1e-3)")
+    p.add_argument("--trust_checkpoint", type=int, default=0,
+                   help="allow unpickling the reference's whole-module checkpoints (train.py:428-432); executes pickle code")
     return p
+
+
+_TRUST = {"on": False}
 
 
 def _load_sd(path):
     from facialmmt_b200.checkpoint import load_state_dict_file
-    return load_state_dict_file(path)
+    return load_state_dict_file(path, trust=_TRUST["on"])
 
 
 def main(argv=None):
     args = build_parser().parse_args(argv)
+    _TRUST["on"] = bool(args.trust_checkpoint)
     if not args.doEval:
         raise SystemExit("facialmmt_b200 implements --doEval (inference) only")
     import torch.distributed as dist
@@ -84,7 +93,7 @@ def main(argv=None):
     labels = torch.randint(0, args.num_labels, (n,), generator=torch.Generator().manual_seed(args.seed))
     results = []
     if args.choice_modality == "V":
-        model = meld_utt_transformer(cfg)
+        model = meld_utt_transformer(cfg, precision=args.precision)
         model.load_state_dict(_load_sd(args.load_unimodal_path) if args.load_unimodal_path
                               else syn.unimodal_stress_state_dict(cfg.fusion, args.seed))
         b = syn.synthetic_batch(cfg, U=n, L=16, seed=args.seed, with_faces=False)
@@ -92,10 +101,10 @@ def main(argv=None):
             u1 = min(hi, u0 + args.trg_batch_size)
             results.append(model(b["vision"][u0:u1], b["vision_mask"][u0:u1]))
     else:
-        swin = SwinForAffwildClassification(cfg)
+        swin = SwinForAffwildClassification(cfg, precision=args.precision)
         swin.load_state_dict(_load_sd(args.load_swin_path) if args.load_swin_path
                              else syn.swin_cls_stress_state_dict(cfg.swin, args.seed))
-        mm = MultiModalTransformerForClassification(cfg)
+        mm = MultiModalTransformerForClassification(cfg, precision=args.precision)
         mm.load_state_dict(_load_sd(args.load_multimodal_path) if args.load_multimodal_path
                            else syn.multimodal_stress_state_dict(cfg, args.seed))
         for u0 in range(lo, hi, args.trg_batch_size):
