@@ -79,6 +79,9 @@ SIGNATURES = {
                                          c_float, c_void_p]),
     "fmmt_op_swin_mlp_pack": (c_int, [c_void_p, c_void_p, c_void_p]),
     "fmmt_op_swin_mlp": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_float, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "fmmt_op_swin_attn_pack": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "fmmt_op_swin_attn": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_void_p,
+                                  c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
     "fmmt_op_swin_mlp_stream": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_float, c_void_p, c_int, c_void_p,
                                         c_void_p, c_int, c_void_p, c_int, c_void_p]),
     "fmmt_op_span_extract": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p,

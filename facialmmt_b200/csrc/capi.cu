@@ -142,10 +142,21 @@ FMMT_API int64_t fmmt_profile_read(fmmt_handle* h, char* buf, int64_t buf_len) {
 }
 
 FMMT_API uint32_t fmmt_debug_timeout(int reset) {
-  const uint32_t a = read_mbar_timeout(reset != 0);
-  const uint32_t b = read_mlp_timeout(reset != 0);
-  const uint32_t c = read_mlp_stream_timeout(reset != 0);
-  return a != 0 ? a : (b != 0 ? b : c);
+  unsigned int* addrs[5] = {watchdog_addr_gemm(), watchdog_addr_mlp96(), watchdog_addr_mlp_stream(), watchdog_addr_attn(),
+                            watchdog_addr_attn96()};
+  cudaDeviceSynchronize();
+  uint32_t first = 0;
+  for (unsigned int* a : addrs) {
+    if (a == nullptr) continue;
+    unsigned int v = 0;
+    if (cudaMemcpy(&v, a, sizeof(v), cudaMemcpyDeviceToHost) != cudaSuccess) continue;
+    if (v != 0 && first == 0) first = v;
+    if (reset && v != 0) {
+      const unsigned int z = 0;
+      cudaMemcpy(a, &z, sizeof(z), cudaMemcpyHostToDevice);
+    }
+  }
+  return first;
 }
 
 FMMT_API int fmmt_debug_umma(const void* a_img, int a_bytes, const void* b_img, int b_bytes, uint64_t adesc_tpl,
@@ -227,6 +238,32 @@ FMMT_API int fmmt_op_swin_mlp(float* x, int M, const float* gamma, const float* 
   a.img = static_cast<const __nv_bfloat16*>(img_dev); a.b1 = b1; a.b2 = b2;
   count_launch();
   return check_cuda(launch_mlp96(a, S(stream)), "fmmt_op_swin_mlp");
+}
+
+FMMT_API int fmmt_op_swin_attn_pack(const float* qkv_w_host, const float* proj_w_host, const float* rel_table_host,
+                                    void* img_dev, float* tab_dev) {
+  if (!qkv_w_host || !proj_w_host || !rel_table_host || !img_dev || !tab_dev)
+    return set_error(FMMT_ERR_INVALID, "fmmt_op_swin_attn_pack: null pointer");
+  std::vector<__nv_bfloat16> img(ATTN96_IMG_BYTES / sizeof(__nv_bfloat16));
+  std::vector<float> tab(ATTN96_TAB_FLOATS);
+  attn96_pack(qkv_w_host, proj_w_host, rel_table_host, img.data(), tab.data());
+  int rc = check_cuda(cudaMemcpy(img_dev, img.data(), ATTN96_IMG_BYTES, cudaMemcpyHostToDevice), "fmmt_op_swin_attn_pack");
+  if (rc != FMMT_OK) return rc;
+  return check_cuda(cudaMemcpy(tab_dev, tab.data(), ATTN96_TAB_FLOATS * sizeof(float), cudaMemcpyHostToDevice),
+                    "fmmt_op_swin_attn_pack");
+}
+
+FMMT_API int fmmt_op_swin_attn(const float* x, float* x_out, int M, int T, const int* gather, const float* gamma,
+                               const float* beta, float eps, const void* img_dev, const float* tab_dev, const float* qkv_b,
+                               const float* proj_b, const int8_t* rid, const int8_t* wflag, int nW, void* stream) {
+  if (!x || !x_out || !gamma || !beta || !img_dev || !tab_dev || !qkv_b || !proj_b)
+    return set_error(FMMT_ERR_INVALID, "fmmt_op_swin_attn: null pointer");
+  Attn96Args a;
+  a.x = x; a.x_out = x_out; a.M = M; a.T = T; a.gather = gather; a.gamma = gamma; a.beta = beta; a.eps = eps;
+  a.img = static_cast<const __nv_bfloat16*>(img_dev); a.tab = tab_dev; a.qkv_b = qkv_b; a.proj_b = proj_b;
+  a.rid = rid; a.wflag = wflag; a.nW = nW;
+  count_launch();
+  return check_cuda(launch_attn96(a, S(stream)), "fmmt_op_swin_attn");
 }
 
 FMMT_API int fmmt_op_swin_mlp_stream(float* x, int M, int C, const float* gamma, const float* beta, float eps,

@@ -204,6 +204,12 @@ void Engine::pack_swin() {
               rid[r++] = static_cast<int8_t>(3 * region(wy * sw.ws + ty) + region(wx * sw.ws + tx));
       sw.rid = dev_alloc<int8_t>(rid.size());
       cudaMemcpy(sw.rid, rid.data(), rid.size(), cudaMemcpyHostToDevice);
+      std::vector<int8_t> wf(sw.nW, 0);
+      for (int w = 0; w < sw.nW; ++w)
+        for (int i = 1; i < sw.N; ++i)
+          if (rid[static_cast<size_t>(w) * sw.N + i] != rid[static_cast<size_t>(w) * sw.N]) wf[w] = 1;
+      sw.wflag = dev_alloc<int8_t>(wf.size());
+      cudaMemcpy(sw.wflag, wf.data(), wf.size(), cudaMemcpyHostToDevice);
     }
     for (int bi = 0; bi < c.depths[li]; ++bi) {
       const std::string p = "swin.layers." + std::to_string(li) + ".blocks." + std::to_string(bi) + ".";
@@ -243,6 +249,16 @@ void Engine::pack_swin() {
       const HostTensor& tab = need(p + "attn.relative_position_bias_table");
       const int span = 2 * sw.ws - 1;
       expect(tab.numel() == static_cast<int64_t>(span) * span * sw.heads, p + "relative_position_bias_table");
+      if (!precise_ && C == ATTN96_C && sw.heads == ATTN96_HEADS && sw.N == ATTN96_N && (T % (2 * ATTN96_N)) == 0 && bw.qkv.b &&
+          bw.proj.b && std::getenv("FMMT_NO_FUSED_ATTN") == nullptr) {
+        std::vector<bf16> img(ATTN96_IMG_BYTES / sizeof(bf16));
+        std::vector<float> tb(ATTN96_TAB_FLOATS);
+        attn96_pack(need(p + "attn.qkv.weight").data.data(), need(p + "attn.proj.weight").data.data(), tab.data.data(),
+                    img.data(), tb.data());
+        bw.attn_img = dev_alloc<bf16>(img.size());
+        cudaMemcpy(bw.attn_img, img.data(), ATTN96_IMG_BYTES, cudaMemcpyHostToDevice);
+        bw.attn_tab = up_f32(tb.data(), tb.size());
+      }
       std::vector<float> be(static_cast<size_t>(sw.heads) * sw.N * sw.N);
       for (int i = 0; i < sw.N; ++i)
         for (int j = 0; j < sw.N; ++j) {
@@ -695,6 +711,24 @@ void Engine::mlp96(float* x, int M, const SwinBlockW& bw) {
   if (prof_) prof_end(e1);
 }
 
+void Engine::attn96(const float* x, float* x_out, int M, const SwinStageW& sw, const SwinBlockW& bw) {
+  if (arena_.dry() || first_err_ != cudaSuccess) return;
+  flops_ += attn96_flops(M);
+  count_launch();
+  cudaEvent_t e1 = nullptr;
+  // algorithmic bytes: x read once, x_out written once, weights
+  if (prof_) e1 = prof_begin("attn_fused C=96 M=" + std::to_string(M), attn96_flops(M), 8.0 * M * ATTN96_C + ATTN96_IMG_BYTES);
+  Attn96Args a;
+  a.x = x; a.x_out = x_out; a.M = M; a.T = sw.R * sw.R;
+  a.gather = bw.identity ? nullptr : bw.gather;
+  a.gamma = bw.ln1.g; a.beta = bw.ln1.b; a.eps = 1e-5f;
+  a.img = bw.attn_img; a.tab = bw.attn_tab; a.qkv_b = bw.qkv.b; a.proj_b = bw.proj.b;
+  a.rid = bw.shift ? sw.rid : nullptr; a.wflag = bw.shift ? sw.wflag : nullptr; a.nW = sw.nW;
+  a.scale = 1.0f / std::sqrt(32.0f);
+  ck(launch_attn96(a, st_), "attn_fused");
+  if (prof_) prof_end(e1);
+}
+
 void Engine::mlp_stream(float* x, int M, int C, const SwinBlockW& bw) {
   if (arena_.dry() || first_err_ != cudaSuccess) return;
   flops_ += mlp_stream_flops(M, C);
@@ -762,9 +796,10 @@ int Engine::run(Fn&& body, cudaStream_t st) {
   body();
   {
     // pipeline watchdog hand-off: collect + clear the per-translation-unit words, copy to the pinned status word
-    unsigned int* addrs[4] = {watchdog_addr_gemm(), watchdog_addr_mlp96(), watchdog_addr_mlp_stream(), watchdog_addr_attn()};
+    unsigned int* addrs[5] = {watchdog_addr_gemm(), watchdog_addr_mlp96(), watchdog_addr_mlp_stream(), watchdog_addr_attn(),
+                              watchdog_addr_attn96()};
     count_launch();
-    ck(launch_collect_status(addrs, 4, status_dev_, st_), "collect_status");
+    ck(launch_collect_status(addrs, 5, status_dev_, st_), "collect_status");
     ck(cudaMemcpyAsync(status_host_, status_dev_, sizeof(unsigned int), cudaMemcpyDeviceToHost, st_), "status copy");
   }
   if (first_err_ != cudaSuccess) return set_error(first_err_ == cudaErrorInvalidValue ? FMMT_ERR_INVALID : FMMT_ERR_CUDA, err_);
@@ -787,6 +822,11 @@ void Engine::capture_block(const std::string& name, const SwinStageW& sw, const 
 void Engine::swin_block(const SwinStageW& sw, const SwinBlockW& bw, float*& x, float*& xalt, int nf, bf16* h, void* qkv,
                         bf16* a, bf16* hid) {
   const int T = sw.R * sw.R, C = sw.C, M = nf * T;
+  if (bw.attn_img != nullptr) {
+    // stage 1: norm1 + gather + qkv + window attention + proj + shortcut in ONE kernel (attn_fused.cu)
+    if (bw.identity) attn96(x, x, M, sw, bw);
+    else { attn96(x, xalt, M, sw, bw); std::swap(x, xalt); }
+  } else {
   LnArgs l1;
   l1.in = x; l1.ld_in = C; l1.M = M; l1.nseg = 1; l1.cseg = C;
   l1.gamma = bw.ln1.g; l1.beta = bw.ln1.b; l1.eps = 1e-5f;
@@ -817,6 +857,7 @@ void Engine::swin_block(const SwinStageW& sw, const SwinBlockW& bw, float*& x, f
   GemmArgs g2;                                                      // proj + shortcut, in window order (no scatter)
   g2.residual = x; g2.ldr = C; g2.out_f32 = x; g2.ldo32 = C;
   gemm_lin(a, C, M, bw.proj, g2);
+  }
   if (bw.mlp_img != nullptr) {                                      // stage 1: norm2 + fc1 + GELU + fc2 + residual fused
     mlp96(x, M, bw);
     return;

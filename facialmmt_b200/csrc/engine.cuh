@@ -10,6 +10,7 @@
 #include <vector>
 
 #include "facialmmt_b200.h"
+#include "attn_fused.cuh"
 #include "gemm.cuh"
 #include "mlp_fused.cuh"
 #include "mlp_stream.cuh"
@@ -47,6 +48,8 @@ struct SwinBlockW {
   Norm ln1, ln2;
   Lin qkv, proj, fc1, fc2;
   bf16* mlp_img = nullptr;    // C == 96: fc1/fc2 pre-swizzled for the fused MLP kernel (mlp_fused.cu), else nullptr
+  bf16* attn_img = nullptr;   // C == 96: qkv/proj pre-swizzled for the fused attention half-block (attn_fused.cu), else nullptr
+  float* attn_tab = nullptr;  //          relative-position bias table [heads][169] * log2(e)
   float* bias_exp = nullptr;  // [heads, N, N]
   int shift = 0;
   // The residual stream is kept in the window order of the most recent attention block, so that every GEMM output
@@ -58,6 +61,7 @@ struct SwinBlockW {
 struct SwinStageW {
   int R = 0, C = 0, heads = 0, ws = 0, N = 0, nW = 0;
   int8_t* rid = nullptr;                 // [nW, N] region ids for shifted blocks
+  int8_t* wflag = nullptr;               // [nW] 1 where a window spans more than one shift region
   std::vector<SwinBlockW> blocks;
   bool has_merge = false;
   int* merge_map = nullptr;  // [T/4, 4] rows of the current stream order (after the stage's last block)
@@ -195,6 +199,7 @@ class Engine {
   void split16(const float* in, int ld_in, bf16* out, int ldp, int M, int C);
   void ln(LnArgs a);
   void mlp96(float* x, int M, const SwinBlockW& bw);
+  void attn96(const float* x, float* x_out, int M, const SwinStageW& sw, const SwinBlockW& bw);
   void mlp_stream(float* x, int M, int C, const SwinBlockW& bw);
   void ck(cudaError_t e, const char* what);
   void capture(const std::string& name, const float* src, size_t count, size_t dst_off = 0);

@@ -155,6 +155,23 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
+// plain bulk copy global -> shared (size multiple of 16), completion on an mbarrier
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(smem_dst)),
+               "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+// shared -> global tile store that ADDS into the destination (fp32 add performed by the memory system)
+__device__ __forceinline__ void tma_reduce_add_f32_2d(const CUtensorMap* tm, const void* smem_src, int c0, int c1) {
+  asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(tm)),
+               "r"(smem_u32(smem_src)), "r"(c0), "r"(c1)
+               : "memory");
+}
+// generic-proxy global writes of this thread become visible to later async-proxy (TMA) accesses
+__device__ __forceinline__ void fence_proxy_async_global() { asm volatile("fence.proxy.async.global;" ::: "memory"); }
+
 // ---------------------------------------------------------------- tcgen05 / TMEM
 __device__ __forceinline__ void tmem_alloc(uint32_t* smem_dst, uint32_t ncols) {  // whole warp
   asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)),
@@ -207,6 +224,22 @@ __device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t (&v)
       : "r"(taddr)
       : "memory");
 }
+// 16 / 8 consecutive fp32 columns (same lane mapping)
+__device__ __forceinline__ void tmem_ld_32x32b_x16(uint32_t taddr, uint32_t* v) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_32x32b_x8(uint32_t taddr, uint32_t* v) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+               : "r"(taddr)
+               : "memory");
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // Shared-memory matrix descriptor for a K-major bf16 operand tile whose rows are 128 bytes (64 bf16) and were
@@ -221,9 +254,23 @@ __device__ __forceinline__ uint64_t make_smem_desc_sw128(uint32_t smem_addr) {
   d |= static_cast<uint64_t>(2) << 61;                     // SWIZZLE_128B
   return d;
 }
+// K-major operand tile with 64-byte rows (32 bf16 per k-block), SWIZZLE_64B: 8-row groups are 512 B apart; 16-byte chunk c
+// of row r lives at chunk c ^ ((r >> 1) & 3) (tile base 512-byte aligned). Pinned by tests/test_umma_layouts_gpu.py.
+__device__ __forceinline__ uint64_t make_smem_desc_sw64(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFF) >> 4);
+  d |= static_cast<uint64_t>(1) << 16;
+  d |= static_cast<uint64_t>(512 >> 4) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(4) << 61;                     // SWIZZLE_64B
+  return d;
+}
+// The same bytes read as an MN-major B operand: rows are the CONTRACTION index (e.g. keys), each row holds 32 contiguous
+// output columns (e.g. head_dim); one k-step of 16 rows is 1024 B. Used with make_idesc_bf16(..., b_mn_major = 1).
 // Instruction descriptor: kind::f16, A/B = bf16 (K-major both), D = fp32, shape M x N.
-__host__ __device__ __forceinline__ uint32_t make_idesc_bf16(int m, int n) {
+__host__ __device__ __forceinline__ uint32_t make_idesc_bf16(int m, int n, int b_mn_major = 0) {
   uint32_t d = 0;
+  d |= static_cast<uint32_t>(b_mn_major & 1) << 16;   // b_major: 0 = K-major, 1 = MN-major
   d |= 1u << 4;                              // c_format = F32
   d |= 1u << 7;                              // a_format = BF16
   d |= 1u << 10;                             // b_format = BF16

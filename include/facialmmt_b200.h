@@ -205,6 +205,22 @@ FMMT_API int fmmt_op_swin_mlp_pack(const float* fc1_w_host, const float* fc2_w_h
 FMMT_API int fmmt_op_swin_mlp(float* x, int M, const float* gamma, const float* beta, float eps, const void* img_dev,
                               const float* b1, const float* b2, void* stream);
 
+/* Fused Swin ATTENTION half-block for C = 96 / 3 heads / 7x7 windows (Swin_Transformer.py:238-264 up to the first residual,
+ * :113-143 WindowAttention.forward), one tcgen05 kernel:
+ *   x_out[r] = x[g(r)] + proj(softmax(scale * q k^T + rel_bias (+ shift mask)) v),   q,k,v = qkv(LayerNorm(x[g(r)]))
+ * x, x_out: fp32 [M, 96] on the device, M = frames * T, T % 98 == 0; rows of x_out are in window order (49 per window);
+ * gather: device int32 [T], window-order row r of a frame reads row gather[r] of that frame in x (roll + window_partition), or
+ * NULL (identity; then x_out may alias x). rid: device int8 [nW, 49] shift-region ids, wflag: device int8 [nW] = window has
+ * more than one region (both NULL for W-MSA). fmmt_op_swin_attn_pack turns qkv.weight (288,96), proj.weight (96,96) and
+ * relative_position_bias_table (169,3) (HOST fp32) into the 73728-byte weight image and the 507-float bias table. */
+#define FMMT_ATTN96_IMG_BYTES 73728
+#define FMMT_ATTN96_TAB_FLOATS 507
+FMMT_API int fmmt_op_swin_attn_pack(const float* qkv_w_host, const float* proj_w_host, const float* rel_table_host,
+                                    void* img_dev, float* tab_dev);
+FMMT_API int fmmt_op_swin_attn(const float* x, float* x_out, int M, int T, const int* gather, const float* gamma,
+                               const float* beta, float eps, const void* img_dev, const float* tab_dev, const float* qkv_b,
+                               const float* proj_b, const int8_t* rid, const int8_t* wflag, int nW, void* stream);
+
 /* Same half-block for C = 192 / 384 (hidden 4C): the weights are streamed from L2 per 128-row tile instead of being
  * resident. w1 = fc1.weight as bf16 [copies * 4C, ldw1], w2 = fc2.weight as bf16 [copies * C, ldw2] (nn.Linear layout,
  * device pointers; `copies` >= 1 identical matrices stacked along the rows, CTA b reads copy b % copies so that the
