@@ -58,6 +58,8 @@ SIGNATURES = {
     "fmmt_filter_pack": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_float, c_int, c_void_p, c_void_p,
                                  c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "fmmt_multimodal_forward": (c_int, [c_void_p] * 9 + [c_int, c_int, c_void_p, c_void_p]),
+    "fmmt_multimodal_forward_dedup": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
+                                              c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p]),
     "fmmt_unimodal_forward": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
     "fmmt_check": (c_int, [c_void_p]),
     "fmmt_set_capture": (c_int, [c_void_p, c_char_p, c_void_p, c_int64]),

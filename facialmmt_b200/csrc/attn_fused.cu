@@ -69,7 +69,13 @@ struct Attn96Params {
   const int8_t* rid; const int8_t* wflag;
   int nW;
   float qscale;      // scale * log2(e)
+  long long* trace;  // optional [8 tiles][32] clock64 stamps of CTA 0 (debug)
 };
+
+#define TRACE(slot)                                                                          \
+  do {                                                                                       \
+    if (p.trace != nullptr && blockIdx.x == 0 && i < 8) p.trace[i * 32 + (slot)] = clock64(); \
+  } while (0)
 
 __device__ __forceinline__ float ex2f(float x) {
   float y;
@@ -163,7 +169,9 @@ swin_attn96_fused_kernel(const __grid_constant__ CUtensorMap tmOut, const Attn96
       mbar_wait(&w_bar, 0, 70);
       for (int i = 0; i < n_local; ++i) {
         const uint32_t par = i & 1u, ppar = par ^ 1u;
+        TRACE(0);
         mbar_wait(&a_full, par, 71);
+        TRACE(1);
         if (i > 0) {   // the S buffers of the previous tile alias the qkv accumulator
           mbar_wait(&s_drained[1], ppar, 72);
           mbar_wait(&s_drained[2], ppar, 72);
@@ -182,11 +190,14 @@ swin_attn96_fused_kernel(const __grid_constant__ CUtensorMap tmOut, const Attn96
         }
         umma_commit(&qkv_full);
         umma_commit(&a_empty);
+        TRACE(2);
         mbar_wait(&qkv_smem_full, par, 73);
+        TRACE(3);
         tc_fence_after();
         issue_s(0);
         issue_s(1);
         mbar_wait(&p_full[0], par, 74);
+        TRACE(4);
         if (i > 0) mbar_wait(&o_drained[2], ppar, 75);
         tc_fence_after();
         issue_pv(0);
@@ -194,14 +205,17 @@ swin_attn96_fused_kernel(const __grid_constant__ CUtensorMap tmOut, const Attn96
         tc_fence_after();
         issue_s(2);
         mbar_wait(&p_full[1], par, 74);
+        TRACE(5);
         if (i > 0) mbar_wait(&o_drained[1], ppar, 75);
         tc_fence_after();
         issue_pv(1);
         mbar_wait(&p_full[2], par, 74);
         mbar_wait(&o_drained[0], par, 75);
+        TRACE(6);
         tc_fence_after();
         issue_pv(2);
         mbar_wait(&o_smem_full, par, 77);
+        TRACE(7);
         if (i > 0) mbar_wait(&proj_drained, ppar, 78);
         tc_fence_after();
 #pragma unroll
@@ -212,6 +226,7 @@ swin_attn96_fused_kernel(const __grid_constant__ CUtensorMap tmOut, const Attn96
           for (int k = 0; k < 2; ++k) umma_bf16(tmem_base + TM_PROJ, a + 2 * k, b + 2 * k, id_96, (kb | k) != 0 ? 1u : 0u);
         }
         umma_commit(&proj_full);
+        TRACE(8);
       }
     }
   } else if (warp < CW0) {
@@ -321,7 +336,9 @@ swin_attn96_fused_kernel(const __grid_constant__ CUtensorMap tmOut, const Attn96
         named_bar_sync(2, 128);
       }
       // ---- qkv accumulator -> (+bias, q * scale * log2 e) -> bf16 Q/K/V tiles
+      if (elected) TRACE(10 + 10 * group);
       mbar_wait(&qkv_full, par, 80);
+      if (elected) TRACE(11 + 10 * group);
       tc_fence_after();
       if (group == 0) s_rid[row] = myrid;
 #pragma unroll 1
@@ -346,12 +363,14 @@ swin_attn96_fused_kernel(const __grid_constant__ CUtensorMap tmOut, const Attn96
       tc_fence_before();
       fence_proxy_async_smem();
       mbar_arrive(&qkv_smem_full);
+      if (elected) TRACE(12 + 10 * group);
 
       // ---- heads of this group: softmax from TMEM -> P tile; O accumulator -> * 1/sum -> O_h tile
 #pragma unroll 1
       for (int h = group; h < 3; h += 2) {
         const int b = h & 1;
         mbar_wait(&s_full[h], par, 81);
+        if (elected) TRACE(13 + 10 * group + (h >> 1) * 3);
         tc_fence_after();
         uint32_t sv[56];
         const uint32_t ts = t_lane + TM_S + static_cast<uint32_t>(b * 128 + win * 64);
@@ -403,8 +422,10 @@ swin_attn96_fused_kernel(const __grid_constant__ CUtensorMap tmOut, const Attn96
         }
         fence_proxy_async_smem();
         mbar_arrive(&p_full[h]);
+        if (elected) TRACE(14 + 10 * group + (h >> 1) * 3);
 
         mbar_wait(&o_full[h], par, 82);
+        if (elected) TRACE(15 + 10 * group + (h >> 1) * 3);
         tc_fence_after();
         uint32_t ov[32];
         tmem_ld_32x32b_x32(t_lane + TM_O + static_cast<uint32_t>(b * 64 + win * 32), ov);
@@ -424,7 +445,9 @@ swin_attn96_fused_kernel(const __grid_constant__ CUtensorMap tmOut, const Attn96
       }
 
       // ---- proj accumulator -> + bias -> 32-column slabs -> TMA reduce-add into x_out (which holds the residual rows)
+      if (elected) TRACE(19 + 10 * group);
       mbar_wait(&proj_full, par, 83);
+      if (elected) TRACE(30 + group);
       tc_fence_after();
 #pragma unroll 1
       for (int s = group; s < 3; s += 2) {
@@ -511,6 +534,7 @@ cudaError_t launch_attn96(const Attn96Args& a, cudaStream_t stream) {
   p.gather = a.gather; p.eps = a.eps; p.img = a.img; p.tab = a.tab; p.qkv_b = a.qkv_b; p.proj_b = a.proj_b;
   p.gamma = a.gamma; p.beta = a.beta; p.rid = a.rid; p.wflag = a.wflag; p.nW = a.nW;
   p.qscale = a.scale * LOG2E;
+  p.trace = a.trace;
   if (a.rid != nullptr && a.wflag == nullptr) return cudaErrorInvalidValue;
   const int grid = p.num_tiles < num_sms ? p.num_tiles : num_sms;
   swin_attn96_fused_kernel<<<grid, THREADS, SMEM_BYTES + 1024, stream>>>(tmOut, p);

@@ -36,6 +36,7 @@ struct Attn96Args {
   const int8_t* wflag = nullptr;    // [nW] 1 where a window spans more than one shift region (needed with rid)
   int nW = 0;                       // windows per frame
   float scale = 0.17677669529663687f;   // head_dim^-0.5 (Swin_Transformer.py:86)
+  long long* trace = nullptr;       // optional device buffer [8][32]: clock64 stamps of CTA 0's first 8 tiles (debug)
 };
 cudaError_t launch_attn96(const Attn96Args& a, cudaStream_t stream);
 inline double attn96_flops(int M) {   // qkv + proj Linear layers + QK^T + PV (2*MAC, algorithmic: 49 keys per query)

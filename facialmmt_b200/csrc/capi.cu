@@ -109,6 +109,17 @@ FMMT_API int fmmt_multimodal_forward(fmmt_handle* h, const int64_t* ids, const i
                                     S(stream));
 }
 
+FMMT_API int fmmt_multimodal_forward_dedup(fmmt_handle* h, const int64_t* ids, const int64_t* mask, int n_dialogues,
+                                           const int32_t* dialogue_of_utt, const int64_t* sep_mask, const float* audio,
+                                           const float* audio_mask, const float* vision, const float* vision_mask,
+                                           const int64_t* idx_in_dia, int U, int L, float* logits, void* stream) {
+  if (!h) return set_error(FMMT_ERR_INVALID, "null handle");
+  if (!dialogue_of_utt || n_dialogues <= 0 || n_dialogues > U)
+    return set_error(FMMT_ERR_INVALID, "fmmt_multimodal_forward_dedup: dialogue_of_utt / n_dialogues");
+  return h->eng->multimodal_forward(ids, mask, sep_mask, audio, audio_mask, vision, vision_mask, idx_in_dia, U, L, logits,
+                                    S(stream), dialogue_of_utt, n_dialogues);
+}
+
 FMMT_API int fmmt_unimodal_forward(fmmt_handle* h, const float* inputs, const float* utt_mask, int U, float* logits,
                                    void* stream) {
   if (!h) return set_error(FMMT_ERR_INVALID, "null handle");
@@ -262,6 +273,8 @@ FMMT_API int fmmt_op_swin_attn(const float* x, float* x_out, int M, int T, const
   a.x = x; a.x_out = x_out; a.M = M; a.T = T; a.gather = gather; a.gamma = gamma; a.beta = beta; a.eps = eps;
   a.img = static_cast<const __nv_bfloat16*>(img_dev); a.tab = tab_dev; a.qkv_b = qkv_b; a.proj_b = proj_b;
   a.rid = rid; a.wflag = wflag; a.nW = nW;
+  // debug hook: nW < 0 -> `stream` carries a device trace buffer [8][32] of clock64 stamps (default stream is used)
+  if (nW < 0) { a.nW = -nW; a.trace = static_cast<long long*>(stream); count_launch(); return check_cuda(launch_attn96(a, nullptr), "fmmt_op_swin_attn"); }
   count_launch();
   return check_cuda(launch_attn96(a, S(stream)), "fmmt_op_swin_attn");
 }
@@ -307,7 +320,7 @@ FMMT_API int fmmt_op_span_extract(const float* text, const int64_t* sep_mask, co
   if (!text || !sep_mask || !idx_in_dia || !out || !out_mask) return set_error(FMMT_ERR_INVALID, "fmmt_op_span_extract: null pointer");
   if (text_kind != FMMT_TEXT_ROBERTA && text_kind != FMMT_TEXT_BERT) return set_error(FMMT_ERR_INVALID, "fmmt_op_span_extract: text_kind");
   count_launch();
-  return check_cuda(launch_span_extract(text, sep_mask, idx_in_dia, U, L, H, max_len, text_kind == FMMT_TEXT_ROBERTA ? 2 : 1,
+  return check_cuda(launch_span_extract(text, sep_mask, idx_in_dia, nullptr, U, L, H, max_len, text_kind == FMMT_TEXT_ROBERTA ? 2 : 1,
                                         out, out_mask, S(stream)),
                     "fmmt_op_span_extract");
 }

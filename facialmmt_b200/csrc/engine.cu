@@ -1142,9 +1142,12 @@ void Engine::pool_head(const float* x32, const bf16* x16, const float* mask01, i
 
 void Engine::multimodal_body(const int64_t* ids, const int64_t* mask, const int64_t* sep, const float* audio,
                              const float* audio_mask, const float* vision, const float* vision_mask, const int64_t* idx,
-                             int U, int L, float* logits) {
+                             int U, int L, float* logits, const int32_t* text_row, int n_text) {
   const fmmt_config& c = cfg_;
-  const int H = c.hidden, D = c.text_hidden, M = U * L;
+  // identical dialogues de-duplicated across the batch: the text encoder runs over the n_text distinct
+  // (ids, mask) rows only; utterance u slices its span out of row text_row[u]. Result-identical (rows are independent).
+  const int Ut = text_row != nullptr ? n_text : U;
+  const int H = c.hidden, D = c.text_hidden, M = Ut * L;
   const int Lt = c.text_len, La = c.audio_len, Lv = c.vision_len;
   // ---- text (src/models.py:99-107)
   int* pos = arena_.alloc<int>(M);
@@ -1153,14 +1156,14 @@ void Engine::multimodal_body(const int64_t* ids, const int64_t* mask, const int6
   float* tmask = arena_.alloc<float>(M);
   if (!arena_.dry() && first_err_ == cudaSuccess) {
     count_launch(2);
-    ck(launch_text_embed(ids, pos, U, L, c.text_kind == FMMT_TEXT_ROBERTA, c.pad_id, text_.word, text_.pos, text_.type0,
+    ck(launch_text_embed(ids, pos, Ut, L, c.text_kind == FMMT_TEXT_ROBERTA, c.pad_id, text_.word, text_.pos, text_.type0,
                          c.max_pos, c.vocab_size, text_.emb_ln.g, text_.emb_ln.b, c.text_eps, D, tx32, tx16, precise_, st_),
        "text_embed");
   }
   OP(launch_cast_i64_f32(mask, tmask, M, st_), "mask cast");
   {
     const size_t mk = arena_.mark();
-    enc_layers(text_.layers, tx32, tx16, U, L, D, c.text_heads, c.text_ffn, tmask, -3.4028234663852886e38f, c.text_eps);
+    enc_layers(text_.layers, tx32, tx16, Ut, L, D, c.text_heads, c.text_ffn, tmask, -3.4028234663852886e38f, c.text_eps);
     arena_.release(mk);
   }
   float* t768 = arena_.alloc<float>(static_cast<size_t>(M) * H);
@@ -1170,7 +1173,7 @@ void Engine::multimodal_body(const int64_t* ids, const int64_t* mask, const int6
   capture("mm.text768", t768, static_cast<size_t>(M) * H);
   float* txt = arena_.alloc<float>(static_cast<size_t>(U) * Lt * H);
   float* txt_mask = arena_.alloc<float>(static_cast<size_t>(U) * Lt);
-  OP(launch_span_extract(t768, sep, idx, U, L, H, Lt, c.text_kind == FMMT_TEXT_ROBERTA ? 2 : 1, txt, txt_mask, st_),
+  OP(launch_span_extract(t768, sep, idx, text_row, U, L, H, Lt, c.text_kind == FMMT_TEXT_ROBERTA ? 2 : 1, txt, txt_mask, st_),
      "span_extract");
   capture("mm.text", txt, static_cast<size_t>(U) * Lt * H);
   // ---- audio / vision self-attention encoders (src/models.py:154-166)
@@ -1205,13 +1208,15 @@ void Engine::multimodal_body(const int64_t* ids, const int64_t* mask, const int6
 
 int Engine::multimodal_forward(const int64_t* ids, const int64_t* mask, const int64_t* sep, const float* audio,
                                const float* audio_mask, const float* vision, const float* vision_mask,
-                               const int64_t* idx, int U, int L, float* logits, cudaStream_t st) {
+                               const int64_t* idx, int U, int L, float* logits, cudaStream_t st, const int32_t* text_row,
+                               int n_text) {
   if (cfg_.model != FMMT_MODEL_MULTIMODAL) return set_error(FMMT_ERR_STATE, "handle is not a multimodal model");
   if (!ids || !mask || !sep || !audio || !audio_mask || !vision || !vision_mask || !idx || !logits)
     return set_error(FMMT_ERR_INVALID, "fmmt_multimodal_forward: null pointer");
   if (U <= 0 || L <= 0 || L > cfg_.max_pos - (cfg_.text_kind == FMMT_TEXT_ROBERTA ? cfg_.pad_id + 1 : 0))
     return set_error(FMMT_ERR_INVALID, "fmmt_multimodal_forward: bad U / L (L exceeds the position table)");
-  return run([&] { multimodal_body(ids, mask, sep, audio, audio_mask, vision, vision_mask, idx, U, L, logits); }, st);
+  return run([&] { multimodal_body(ids, mask, sep, audio, audio_mask, vision, vision_mask, idx, U, L, logits, text_row, n_text); },
+             st);
 }
 
 void Engine::unimodal_body(const float* inputs, const float* mask, int U, float* logits) {

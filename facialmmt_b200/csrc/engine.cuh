@@ -152,7 +152,7 @@ class Engine {
                       float* probs, float* importance, float* feat, cudaStream_t st);
   int multimodal_forward(const int64_t* ids, const int64_t* mask, const int64_t* sep, const float* audio,
                          const float* audio_mask, const float* vision, const float* vision_mask, const int64_t* idx,
-                         int U, int L, float* logits, cudaStream_t st);
+                         int U, int L, float* logits, cudaStream_t st, const int32_t* text_row = nullptr, int n_text = 0);
   int unimodal_forward(const float* inputs, const float* mask, int U, float* logits, cudaStream_t st);
   int set_capture(const char* name, float* dst, int64_t count);
   // Per-kernel CUDA-event timing (on the launch stream) for roofline accounting; adds two event records per launch.
@@ -223,7 +223,7 @@ class Engine {
   void pool_head(const float* x32, const bf16* x16, const float* mask01, int U, int L, float* logits);
   void multimodal_body(const int64_t* ids, const int64_t* mask, const int64_t* sep, const float* audio,
                        const float* audio_mask, const float* vision, const float* vision_mask, const int64_t* idx, int U,
-                       int L, float* logits);
+                       int L, float* logits, const int32_t* text_row, int n_text);
   void unimodal_body(const float* inputs, const float* mask, int U, float* logits);
   template <typename Fn> int run(Fn&& body, cudaStream_t st);
 

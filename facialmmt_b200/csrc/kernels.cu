@@ -439,11 +439,13 @@ __global__ void __launch_bounds__(256) text_embed_ln_kernel(const int64_t* __res
 // ------------------------------------------------------------------------------------------------ span extraction
 __global__ void __launch_bounds__(256) span_extract_kernel(const float* __restrict__ text,
                                                            const int64_t* __restrict__ sep_mask,
-                                                           const int64_t* __restrict__ idx_in_dia, int L, int H,
+                                                           const int64_t* __restrict__ idx_in_dia,
+                                                           const int* __restrict__ text_row, int L, int H,
                                                            int max_len, int gap, float* __restrict__ out,
                                                            float* __restrict__ out_mask) {
   __shared__ int s_start, s_n;
   const int u = blockIdx.x;
+  const int tr = text_row != nullptr ? text_row[u] : u;   // de-duplicated dialogues: row of `text` that holds u's dialogue
   if (threadIdx.x == 0) {
     const long long p = idx_in_dia[u];
     int start = 0, n = 0, seen = 0, prev = -1;
@@ -469,7 +471,7 @@ __global__ void __launch_bounds__(256) span_extract_kernel(const float* __restri
   for (int idx = threadIdx.x; idx < max_len * hv; idx += blockDim.x) {
     const int row = idx / hv, c4 = idx - row * hv;
     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (row < n) v = *reinterpret_cast<const float4*>(text + (static_cast<size_t>(u) * L + start + row) * H + c4 * 4);
+    if (row < n) v = *reinterpret_cast<const float4*>(text + (static_cast<size_t>(tr) * L + start + row) * H + c4 * 4);
     *reinterpret_cast<float4*>(out + (static_cast<size_t>(u) * max_len + row) * H + c4 * 4) = v;
   }
   for (int row = threadIdx.x; row < max_len; row += blockDim.x)
@@ -695,10 +697,10 @@ cudaError_t launch_text_embed(const int64_t* ids, int* pos_scratch, int U, int L
   return cudaGetLastError();
 }
 
-cudaError_t launch_span_extract(const float* text, const int64_t* sep_mask, const int64_t* idx_in_dia, int U, int L,
-                                int H, int max_len, int gap, float* out, float* out_mask, cudaStream_t stream) {
+cudaError_t launch_span_extract(const float* text, const int64_t* sep_mask, const int64_t* idx_in_dia, const int* text_row,
+                                int U, int L, int H, int max_len, int gap, float* out, float* out_mask, cudaStream_t stream) {
   if (U <= 0 || (H % 4) != 0) return cudaErrorInvalidValue;
-  span_extract_kernel<<<U, 256, 0, stream>>>(text, sep_mask, idx_in_dia, L, H, max_len, gap, out, out_mask);
+  span_extract_kernel<<<U, 256, 0, stream>>>(text, sep_mask, idx_in_dia, text_row, L, H, max_len, gap, out, out_mask);
   return cudaGetLastError();
 }
 

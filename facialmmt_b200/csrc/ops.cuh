@@ -87,8 +87,9 @@ cudaError_t launch_text_embed(const int64_t* ids, int* pos_scratch, int U, int L
                               __nv_bfloat16* out_bf16, int split, cudaStream_t stream);
 
 // Utterance span extraction (src/models.py:112-150): text [U,L,H] -> out [U,max_len,H] (+0/1 mask)
-cudaError_t launch_span_extract(const float* text, const int64_t* sep_mask, const int64_t* idx_in_dia, int U, int L,
-                                int H, int max_len, int gap, float* out, float* out_mask, cudaStream_t stream);
+//   text_row (optional, int32 [U]): utterance u slices row text_row[u] of `text` (dialogues de-duplicated across the batch)
+cudaError_t launch_span_extract(const float* text, const int64_t* sep_mask, const int64_t* idx_in_dia, const int* text_row,
+                                int U, int L, int H, int max_len, int gap, float* out, float* out_mask, cudaStream_t stream);
 
 // CrossModal embed: out = sqrt(H)*x + sinusoid[pos], pos = t+1 if x[...,0] != 0 else 0 (position_embedding.py:8-27)
 cudaError_t launch_cmt_embed(const float* x, int rows_in, int rows_total, int row_off, const float* table, int U,

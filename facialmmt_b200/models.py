@@ -306,6 +306,8 @@ class MultiModalTransformerForClassification(_Module):
     def _spec(self):
         return _syn.multimodal_state_dict_spec(self.cfg)
 
+    dedup_dialogues = True   # encode identical (ids, mask) rows of a batch once (host tensors only; result-identical)
+
     def forward(self, batch_text_input_ids=None, batch_text_input_mask=None, batch_text_sep_mask=None,
                 audio_inputs=None, audio_mask=None, vision_inputs=None, new_vision_mask=None,
                 batchUtt_in_dia_idx=None):
@@ -313,14 +315,28 @@ class MultiModalTransformerForClassification(_Module):
         if not self._finalized:
             raise _lib.FmmtError("load_state_dict() must be called before forward()")
         f = self.cfg.fusion
-        ids, msk, sep = _i64(batch_text_input_ids), _i64(batch_text_input_mask), _i64(batch_text_sep_mask)
         U = vision_inputs.shape[0]                                   # utt_batch_size (src/models.py:112)
+        row_of_utt = None
+        if (self.dedup_dialogues and U > 1 and not batch_text_input_ids.is_cuda and not batch_text_input_mask.is_cuda
+                and tuple(batch_text_input_ids.shape) == tuple(batch_text_input_mask.shape)
+                and batch_text_input_ids.shape[0] == U):
+            # MELD encodes an utterance with its whole dialogue (src/meld_bert_extraText.py:65-130): consecutive utterances of
+            # an eval batch share their ids/mask rows. Host tensors (what the DataLoader yields) are compared for free.
+            both = torch.cat([batch_text_input_ids.to(torch.int64), batch_text_input_mask.to(torch.int64)], dim=1)
+            uniq, inverse = torch.unique(both, dim=0, return_inverse=True)
+            if uniq.shape[0] < U:
+                Lr = batch_text_input_ids.shape[1]
+                batch_text_input_ids, batch_text_input_mask = uniq[:, :Lr].contiguous(), uniq[:, Lr:].contiguous()
+                row_of_utt = inverse.to(torch.int32).to("cuda", non_blocking=True)
+        ids, msk, sep = _i64(batch_text_input_ids), _i64(batch_text_input_mask), _i64(batch_text_sep_mask)
+        Ud = ids.shape[0]
         L = ids.shape[1]
         if isinstance(batchUtt_in_dia_idx, (list, tuple)):
             batchUtt_in_dia_idx = torch.tensor(list(batchUtt_in_dia_idx))
         idx = _i64(batchUtt_in_dia_idx)
         a, am, v, vm = _f32(audio_inputs), _f32(audio_mask), _f32(vision_inputs), _f32(new_vision_mask)
-        if tuple(ids.shape) != (U, L) or tuple(msk.shape) != (U, L) or tuple(sep.shape) != (U, L):
+        if tuple(ids.shape) != (Ud, L) or tuple(msk.shape) != (Ud, L) or tuple(sep.shape) != (U, L) or \
+                (row_of_utt is None and Ud != U):
             raise ValueError("text tensors must be (U, L)")
         if tuple(a.shape) != (U, f.audio_len, f.audio_dim) or tuple(am.shape) != (U, f.audio_len):
             raise ValueError(f"audio must be (U,{f.audio_len},{f.audio_dim}) with mask (U,{f.audio_len})")
@@ -329,9 +345,15 @@ class MultiModalTransformerForClassification(_Module):
         if idx.numel() != U:
             raise ValueError("batchUtt_in_dia_idx must have U entries")
         logits = torch.empty(U, f.num_labels, device="cuda", dtype=torch.float32)
-        _lib.check(self._lib.fmmt_multimodal_forward(self._h, _lib.ptr(ids), _lib.ptr(msk), _lib.ptr(sep), _lib.ptr(a),
-                                                     _lib.ptr(am), _lib.ptr(v), _lib.ptr(vm), _lib.ptr(idx), U, L,
-                                                     _lib.ptr(logits), _lib.cur_stream()), "fmmt_multimodal_forward")
+        if row_of_utt is not None:
+            _lib.check(self._lib.fmmt_multimodal_forward_dedup(self._h, _lib.ptr(ids), _lib.ptr(msk), Ud, _lib.ptr(row_of_utt),
+                                                               _lib.ptr(sep), _lib.ptr(a), _lib.ptr(am), _lib.ptr(v),
+                                                               _lib.ptr(vm), _lib.ptr(idx), U, L, _lib.ptr(logits),
+                                                               _lib.cur_stream()), "fmmt_multimodal_forward_dedup")
+        else:
+            _lib.check(self._lib.fmmt_multimodal_forward(self._h, _lib.ptr(ids), _lib.ptr(msk), _lib.ptr(sep), _lib.ptr(a),
+                                                         _lib.ptr(am), _lib.ptr(v), _lib.ptr(vm), _lib.ptr(idx), U, L,
+                                                         _lib.ptr(logits), _lib.cur_stream()), "fmmt_multimodal_forward")
         return logits
 
 
