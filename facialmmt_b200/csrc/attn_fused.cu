@@ -13,12 +13,13 @@
 //   * one thread issues every tcgen05.mma: qkv (N = 192 + 96, K = 96) -> TMEM; per head S = Q_h K_h^T (M = 128, N = 128,
 //     K = 32: both windows in one instruction, each row reads its own window's 64-column half); O_h = P_h V_h as two
 //     N = 32, K = 64 instructions (one per window) with V_h read in place as an MN-major operand; proj (N = 96, K = 96);
-//   * 8 compute warps in two groups drain qkv (+bias, q * scale * log2 e) into per-head Q/K/V tiles, run the softmax from
-//     TMEM (relative-position bias from a 2 KB [head][169] table, shift mask from region ids, exp2, fp32), write P as a
-//     bf16 K-major tile, scale O by 1/sum into the tile that held Q_h, and hand the proj accumulator (+bias) to TMA
-//     reduce-add (cp.reduce.async.bulk.tensor .add) which applies the residual in the memory system.
-// TMEM columns: [0,288) qkv accumulator, re-used as two 128-column S buffers; [288,416) two O buffers (2 x 32 per head);
-// [416,512) proj accumulator.
+//   * 12 compute warps in three groups, ONE GROUP PER HEAD, drain q_h / k_h / v_h (+bias, q * scale * log2 e) into the
+//     head's Q/K/V tiles, run the softmax from TMEM (relative-position bias from a 2 KB [head][169] table, shift mask from
+//     region ids, exp2, fp32), write P_h as a bf16 K-major tile, scale O_h by 1/sum into the tile that held Q_h, and hand
+//     32 columns of the proj accumulator (+bias) to TMA reduce-add (cp.reduce.async.bulk.tensor .add), which applies the
+//     residual in the memory system.
+// TMEM columns: [0,288) qkv accumulator, re-used as three 128-column S_h buffers [0,384) whose first 64 columns are re-used
+// again for O_h (2 x 32, one per window); [416,512) proj accumulator.
 #include "attn_fused.cuh"
 
 #include <mutex>
@@ -36,8 +37,8 @@ constexpr int NTOK = ATTN96_N;
 constexpr int TILE_TOK = 2 * NTOK;              // 98 valid rows per tile
 constexpr int MMA_WARP = 0;
 constexpr int LN_WARP0 = 1, LN_WARPS = 8;       // warps 1..8
-constexpr int CW0 = LN_WARP0 + LN_WARPS;        // compute warps 9..16: group 0 = 9..12, group 1 = 13..16
-constexpr int THREADS = (CW0 + 8) * 32;         // 544
+constexpr int CW0 = LN_WARP0 + LN_WARPS;        // compute warps 9..20: group h = warps 9 + 4h .. 12 + 4h = head h
+constexpr int THREADS = (CW0 + 12) * 32;        // 672
 
 constexpr int WQKV_KB = 288 * 64;               // bytes of one 32-channel k-block of qkv.weight
 constexpr int WPROJ_KB = 96 * 64;
@@ -45,17 +46,16 @@ constexpr int OFF_W = 0;
 constexpr int OFF_WPROJ = 3 * WQKV_KB;          // 55296
 constexpr int OFF_A = ATTN96_IMG_BYTES;         // 73728: three [128 x 64 B] k-blocks
 constexpr int OFF_QKV = OFF_A + 3 * 8192;       // 98304: nine [128 x 64 B] tiles Q0 Q1 Q2 K0 K1 K2 V0 V1 V2 (O_h re-uses Q_h)
-constexpr int OFF_P = OFF_QKV + 9 * 8192;       // 172032: two [128 x 128 B] probability tiles
-constexpr int OFF_SLAB = OFF_P + 2 * 16384;     // 204800: [128 x 32] fp32 output slab of group 0 (group 1 uses P[1])
-constexpr int OFF_TAB = OFF_SLAB + 16384;       // 221184: bias table [3][169] fp32 (pre-multiplied by log2 e)
+constexpr int OFF_P = OFF_QKV + 9 * 8192;       // 172032: three [128 x 128 B] probability tiles P_h; P_h doubles as group h's
+                                                //         [128 x 32] fp32 output slab once its P V products are done
+constexpr int OFF_TAB = OFF_P + 3 * 16384;      // 221184: bias table [3][169] fp32 (pre-multiplied by log2 e)
 constexpr int OFF_VEC = OFF_TAB + 2048;         // qkv bias [288] | proj bias [96] | gamma [96] | beta [96]
 constexpr int OFF_RID = OFF_VEC + 576 * 4;      // region id per tile row [128] int8
 constexpr int SMEM_BYTES = OFF_RID + 128;       // 225664
 static_assert(SMEM_BYTES + 1024 <= 227 * 1024, "shared memory budget");
 
-constexpr uint32_t TM_S = 0;        // S buffer b at 128 b
+constexpr uint32_t TM_S = 0;        // S_h at 128 h; O_h (window w) at 128 h + 32 w once the softmax has read S_h
 constexpr uint32_t TM_V = 192;      // v part of the qkv accumulator
-constexpr uint32_t TM_O = 288;      // O buffer b, window w at 288 + 64 b + 32 w
 constexpr uint32_t TM_PROJ = 416;
 constexpr float LOG2E = 1.4426950408889634f;
 
@@ -86,8 +86,8 @@ __device__ __forceinline__ float ex2f(float x) {
 __global__ void __launch_bounds__(THREADS, 1)
 swin_attn96_fused_kernel(const __grid_constant__ CUtensorMap tmOut, const Attn96Params p) {
   extern __shared__ uint8_t smem_raw[];
-  __shared__ uint64_t w_bar, a_full, a_empty, qkv_full, qkv_smem_full, o_smem_full, proj_full, proj_drained;
-  __shared__ uint64_t s_full[3], s_drained[3], p_full[3], o_full[3], o_drained[3];
+  __shared__ uint64_t w_bar, a_full, a_empty, qkv_full, qkv_ready, o_smem_full, proj_full, proj_drained;
+  __shared__ uint64_t s_full[3], p_full[3], o_full[3], o_drained[3];
   __shared__ uint32_t tmem_base_slot;
 
   const int warp = threadIdx.x >> 5;
@@ -103,13 +103,12 @@ swin_attn96_fused_kernel(const __grid_constant__ CUtensorMap tmOut, const Attn96
     mbar_init(&a_full, LN_WARPS * 32);
     mbar_init(&a_empty, 1);
     mbar_init(&qkv_full, 1);
-    mbar_init(&qkv_smem_full, 256);
+    mbar_init(&qkv_ready, 384);
     mbar_init(&o_smem_full, 384);
     mbar_init(&proj_full, 1);
-    mbar_init(&proj_drained, 256);
+    mbar_init(&proj_drained, 384);
     for (int h = 0; h < 3; ++h) {
       mbar_init(&s_full[h], 1);
-      mbar_init(&s_drained[h], 128);
       mbar_init(&p_full[h], 128);
       mbar_init(&o_full[h], 1);
       mbar_init(&o_drained[h], 128);
@@ -149,32 +148,42 @@ swin_attn96_fused_kernel(const __grid_constant__ CUtensorMap tmOut, const Attn96
       auto issue_s = [&](int h) {
         const uint64_t a = make_smem_desc_sw64(smem_base + OFF_QKV + h * 8192);
         const uint64_t b = make_smem_desc_sw64(smem_base + OFF_QKV + (3 + h) * 8192);
-        const uint32_t d = tmem_base + TM_S + static_cast<uint32_t>((h & 1) * 128);
+        const uint32_t d = tmem_base + TM_S + static_cast<uint32_t>(h * 128);
         umma_bf16(d, a, b, id_s, 0u);
         umma_bf16(d, a + 2, b + 2, id_s, 1u);
         umma_commit(&s_full[h]);
       };
-      auto issue_pv = [&](int h) {
-        const uint64_t a = make_smem_desc_sw128(smem_base + OFF_P + (h & 1) * 16384);
+      // O_h = P_h V_h for the three heads and both windows: six independent accumulators, issued interleaved so that
+      // consecutive instructions never wait for each other's accumulator (a dependent chain costs ~100 cycles per link)
+      auto issue_pv_all = [&]() {
+        uint64_t a[3], b[3][2];
 #pragma unroll
-        for (int w = 0; w < 2; ++w) {
-          // V_h rows 64 w .. 64 w + 63 are window w's keys; MN-major: one k-step of 16 keys = 1024 B
-          const uint64_t b = make_smem_desc_sw64(smem_base + OFF_QKV + (6 + h) * 8192 + w * 4096);
-          const uint32_t d = tmem_base + TM_O + static_cast<uint32_t>((h & 1) * 64 + w * 32);
+        for (int h = 0; h < 3; ++h) {
+          a[h] = make_smem_desc_sw128(smem_base + OFF_P + h * 16384);
 #pragma unroll
-          for (int k = 0; k < 4; ++k) umma_bf16(d, a + 2 * k, b + 64 * k, id_pv, k != 0 ? 1u : 0u);
+          for (int w = 0; w < 2; ++w)   // V_h rows 64 w .. 64 w + 63 are window w's keys; MN-major: 16 keys = 1024 B
+            b[h][w] = make_smem_desc_sw64(smem_base + OFF_QKV + (6 + h) * 8192 + w * 4096);
         }
-        umma_commit(&o_full[h]);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+#pragma unroll
+          for (int h = 0; h < 3; ++h)
+#pragma unroll
+            for (int w = 0; w < 2; ++w)
+              umma_bf16(tmem_base + TM_S + static_cast<uint32_t>(h * 128 + w * 32), a[h] + 2 * k, b[h][w] + 64 * k, id_pv,
+                        k != 0 ? 1u : 0u);   // O_h over the consumed S_h
+#pragma unroll
+        for (int h = 0; h < 3; ++h) umma_commit(&o_full[h]);
       };
       mbar_wait(&w_bar, 0, 70);
       for (int i = 0; i < n_local; ++i) {
         const uint32_t par = i & 1u, ppar = par ^ 1u;
         TRACE(0);
-        mbar_wait(&a_full, par, 71);
+        mbar_wait_relaxed(&a_full, par, 71, 1000);
         TRACE(1);
-        if (i > 0) {   // the S buffers of the previous tile alias the qkv accumulator
-          mbar_wait(&s_drained[1], ppar, 72);
-          mbar_wait(&s_drained[2], ppar, 72);
+        if (i > 0) {   // S_h / O_h of the previous tile alias the qkv accumulator
+#pragma unroll
+          for (int h = 0; h < 3; ++h) mbar_wait(&o_drained[h], ppar, 72);
         }
         tc_fence_after();
 #pragma unroll
@@ -191,30 +200,20 @@ swin_attn96_fused_kernel(const __grid_constant__ CUtensorMap tmOut, const Attn96
         umma_commit(&qkv_full);
         umma_commit(&a_empty);
         TRACE(2);
-        mbar_wait(&qkv_smem_full, par, 73);
+        mbar_wait_relaxed(&qkv_ready, par, 73, 1000);     // every group has read its accumulator columns and written its Q/K/V tiles
         TRACE(3);
         tc_fence_after();
         issue_s(0);
         issue_s(1);
-        mbar_wait(&p_full[0], par, 74);
-        TRACE(4);
-        if (i > 0) mbar_wait(&o_drained[2], ppar, 75);
-        tc_fence_after();
-        issue_pv(0);
-        mbar_wait(&s_drained[0], par, 76);
-        tc_fence_after();
         issue_s(2);
-        mbar_wait(&p_full[1], par, 74);
-        TRACE(5);
-        if (i > 0) mbar_wait(&o_drained[1], ppar, 75);
+#pragma unroll
+        for (int h = 0; h < 3; ++h) {
+          mbar_wait_relaxed(&p_full[h], par, 74, 1000);   // P_h written; S_h read out (its columns may take O_h)
+          TRACE(4 + h);
+        }
         tc_fence_after();
-        issue_pv(1);
-        mbar_wait(&p_full[2], par, 74);
-        mbar_wait(&o_drained[0], par, 75);
-        TRACE(6);
-        tc_fence_after();
-        issue_pv(2);
-        mbar_wait(&o_smem_full, par, 77);
+        issue_pv_all();
+        mbar_wait_relaxed(&o_smem_full, par, 77, 1000);
         TRACE(7);
         if (i > 0) mbar_wait(&proj_drained, ppar, 78);
         tc_fence_after();
@@ -308,18 +307,34 @@ swin_attn96_fused_kernel(const __grid_constant__ CUtensorMap tmOut, const Attn96
       mbar_arrive(&a_full);
     }
   } else {
-    // ------------------------------------------------------------------ compute warps
+    // ------------------------------------------------------------------ compute warps: group h owns head h
     const int cw = warp - CW0;
-    const int group = cw >> 2;                 // group 0: heads 0, 2; group 1: head 1
+    const int h = cw >> 2;
     const int quarter = warp & 3;              // TMEM lane quarter this warp may access
     const int row = quarter * 32 + lane;
     const int win = row >> 6, tok = row & 63;
     const bool valid = tok < NTOK;
     const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
     const int sw64 = (row >> 1) & 3, sw128 = row & 7;
-    const bool elected = lane == 0 && quarter == ((CW0 + 4 * group) & 3);   // first warp of the group
-    uint8_t* slab = smem + (group == 0 ? OFF_SLAB : OFF_P + 16384);
+    const bool elected = lane == 0 && (cw & 3) == 0;   // first warp of the group
+    uint8_t* ptile = smem + OFF_P + h * 16384;         // P_h, later this group's output slab
     const int bias_base = (tok / 7 + 6) * 13 + (tok % 7) + 6;
+    const float* tb = s_tab + h * 169 + bias_base;
+    // one accumulator unit (32 columns of this row) -> + bias (-> * mul) -> bf16 -> 64-byte row of a SWIZZLE_64B tile
+    auto store_unit = [&](const uint32_t (&v)[32], int u, float mul) {
+      const float* bias = s_vec + 32 * u;
+      uint8_t* dst = smem + OFF_QKV + u * 8192 + row * 64;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const float4 b0 = *reinterpret_cast<const float4*>(bias + 8 * c);
+        const float4 b1 = *reinterpret_cast<const float4*>(bias + 8 * c + 4);
+        *reinterpret_cast<uint4*>(dst + ((c ^ sw64) << 4)) = make_uint4(
+            pack_bf16((__uint_as_float(v[8 * c + 0]) + b0.x) * mul, (__uint_as_float(v[8 * c + 1]) + b0.y) * mul),
+            pack_bf16((__uint_as_float(v[8 * c + 2]) + b0.z) * mul, (__uint_as_float(v[8 * c + 3]) + b0.w) * mul),
+            pack_bf16((__uint_as_float(v[8 * c + 4]) + b1.x) * mul, (__uint_as_float(v[8 * c + 5]) + b1.y) * mul),
+            pack_bf16((__uint_as_float(v[8 * c + 6]) + b1.z) * mul, (__uint_as_float(v[8 * c + 7]) + b1.w) * mul));
+      }
+    };
     for (int i = 0; i < n_local; ++i) {
       const int tile = static_cast<int>(blockIdx.x) + i * static_cast<int>(gridDim.x);
       const uint32_t par = i & 1u;
@@ -331,71 +346,56 @@ swin_attn96_fused_kernel(const __grid_constant__ CUtensorMap tmOut, const Attn96
         masked = __ldg(p.wflag + wi) != 0;
         if (valid) myrid = __ldg(p.rid + wi * NTOK + tok);
       }
-      if (group == 1) {   // P[1] doubles as this group's output slab: the previous tile's reduce-add must have read it
-        if (elected) tma_store_wait_read<0>();
-        named_bar_sync(2, 128);
-      }
-      // ---- qkv accumulator -> (+bias, q * scale * log2 e) -> bf16 Q/K/V tiles
-      if (elected) TRACE(10 + 10 * group);
-      mbar_wait(&qkv_full, par, 80);
-      if (elected) TRACE(11 + 10 * group);
+      // P_h doubled as the output slab of the previous tile: its reduce-add must have read it before P_h is rewritten
+      if (elected) tma_store_wait_read<0>();
+      named_bar_sync(1 + h, 128);
+      // ---- q_h, k_h, v_h accumulator columns -> (+bias, q * scale * log2 e) -> bf16 tiles (loads run one unit ahead)
+      if (elected) TRACE(10 + 7 * h);
+      mbar_wait_relaxed(&qkv_full, par, 80, 1000);
+      if (elected) TRACE(11 + 7 * h);
       tc_fence_after();
-      if (group == 0) s_rid[row] = myrid;
-#pragma unroll 1
-      for (int u = group; u < 9; u += 2) {
-        uint32_t v[32];
-        tmem_ld_32x32b_x32(t_lane + static_cast<uint32_t>(32 * u), v);
+      if (h == 0) s_rid[row] = myrid;
+      {
+        uint32_t va[32], vb[32];
+        tmem_ld_32x32b_x32(t_lane + static_cast<uint32_t>(32 * h), va);
         tmem_ld_wait();
-        const float* bias = s_vec + 32 * u;
-        const float mul = u < 3 ? p.qscale : 1.0f;
-        uint8_t* dst = smem + OFF_QKV + u * 8192 + row * 64;
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          const float4 b0 = *reinterpret_cast<const float4*>(bias + 8 * c);
-          const float4 b1 = *reinterpret_cast<const float4*>(bias + 8 * c + 4);
-          *reinterpret_cast<uint4*>(dst + ((c ^ sw64) << 4)) = make_uint4(
-              pack_bf16((__uint_as_float(v[8 * c + 0]) + b0.x) * mul, (__uint_as_float(v[8 * c + 1]) + b0.y) * mul),
-              pack_bf16((__uint_as_float(v[8 * c + 2]) + b0.z) * mul, (__uint_as_float(v[8 * c + 3]) + b0.w) * mul),
-              pack_bf16((__uint_as_float(v[8 * c + 4]) + b1.x) * mul, (__uint_as_float(v[8 * c + 5]) + b1.y) * mul),
-              pack_bf16((__uint_as_float(v[8 * c + 6]) + b1.z) * mul, (__uint_as_float(v[8 * c + 7]) + b1.w) * mul));
-        }
+        tmem_ld_32x32b_x32(t_lane + static_cast<uint32_t>(32 * (3 + h)), vb);
+        store_unit(va, h, p.qscale);
+        tmem_ld_wait();
+        tmem_ld_32x32b_x32(t_lane + static_cast<uint32_t>(32 * (6 + h)), va);
+        store_unit(vb, 3 + h, 1.0f);
+        tmem_ld_wait();
+        store_unit(va, 6 + h, 1.0f);
       }
       tc_fence_before();
       fence_proxy_async_smem();
-      mbar_arrive(&qkv_smem_full);
-      if (elected) TRACE(12 + 10 * group);
+      mbar_arrive(&qkv_ready);
+      if (elected) TRACE(12 + 7 * h);
 
-      // ---- heads of this group: softmax from TMEM -> P tile; O accumulator -> * 1/sum -> O_h tile
-#pragma unroll 1
-      for (int h = group; h < 3; h += 2) {
-        const int b = h & 1;
-        mbar_wait(&s_full[h], par, 81);
-        if (elected) TRACE(13 + 10 * group + (h >> 1) * 3);
-        tc_fence_after();
+      // ---- softmax of head h from TMEM -> P_h
+      mbar_wait_relaxed(&s_full[h], par, 81, 1000);
+      if (elected) TRACE(13 + 7 * h);
+      tc_fence_after();
+      float inv = 0.f;
+      {
         uint32_t sv[56];
-        const uint32_t ts = t_lane + TM_S + static_cast<uint32_t>(b * 128 + win * 64);
+        const uint32_t ts = t_lane + TM_S + static_cast<uint32_t>(h * 128 + win * 64);
         tmem_ld_32x32b_x32(ts, reinterpret_cast<uint32_t(&)[32]>(sv[0]));
         tmem_ld_32x32b_x16(ts + 32u, sv + 32);
         tmem_ld_32x32b_x8(ts + 48u, sv + 48);
         tmem_ld_wait();
-        tc_fence_before();
-        mbar_arrive(&s_drained[h]);
-        float inv = 0.f;
+        tc_fence_before();      // S_h is read out: its columns may receive O_h once p_full[h] completes
         if (valid) {
           // scores are already in the log2 domain (q carries scale * log2 e; the table is pre-multiplied by log2 e)
-          const float* tb = s_tab + h * 169 + bias_base;
-          float mx = -INFINITY;
 #pragma unroll
-          for (int j = 0; j < NTOK; ++j) {
-            float s = __uint_as_float(sv[j]) + tb[-((j / 7) * 13 + (j % 7))];
-            sv[j] = __float_as_uint(s);
-          }
+          for (int j = 0; j < NTOK; ++j) sv[j] = __float_as_uint(__uint_as_float(sv[j]) + tb[-((j / 7) * 13 + (j % 7))]);
           if (masked) {
             const int8_t* rw = s_rid + win * 64;
 #pragma unroll
             for (int j = 0; j < NTOK; ++j)
               if (rw[j] != myrid) sv[j] = __float_as_uint(__uint_as_float(sv[j]) - 100.0f * LOG2E);
           }
+          float mx = -INFINITY;
 #pragma unroll
           for (int j = 0; j < NTOK; ++j) mx = fmaxf(mx, __uint_as_float(sv[j]));
           float sum = 0.f;
@@ -406,7 +406,7 @@ swin_attn96_fused_kernel(const __grid_constant__ CUtensorMap tmOut, const Attn96
             sv[j] = __float_as_uint(e);
           }
           inv = __fdividef(1.0f, sum);
-          uint8_t* prow = smem + OFF_P + b * 16384 + row * 128;
+          uint8_t* prow = ptile + row * 128;
 #pragma unroll
           for (int c = 0; c < 8; ++c) {
             uint32_t w4[4];
@@ -420,19 +420,22 @@ swin_attn96_fused_kernel(const __grid_constant__ CUtensorMap tmOut, const Attn96
             *reinterpret_cast<uint4*>(prow + ((c ^ sw128) << 4)) = make_uint4(w4[0], w4[1], w4[2], w4[3]);
           }
         }
-        fence_proxy_async_smem();
-        mbar_arrive(&p_full[h]);
-        if (elected) TRACE(14 + 10 * group + (h >> 1) * 3);
+      }
+      fence_proxy_async_smem();
+      mbar_arrive(&p_full[h]);
+      if (elected) TRACE(14 + 7 * h);
 
-        mbar_wait(&o_full[h], par, 82);
-        if (elected) TRACE(15 + 10 * group + (h >> 1) * 3);
-        tc_fence_after();
+      // ---- O_h accumulator -> * 1/sum -> bf16 -> the tile that held Q_h (S_h has consumed it): A operand of proj
+      mbar_wait_relaxed(&o_full[h], par, 82, 1000);
+      if (elected) TRACE(15 + 7 * h);
+      tc_fence_after();
+      {
         uint32_t ov[32];
-        tmem_ld_32x32b_x32(t_lane + TM_O + static_cast<uint32_t>(b * 64 + win * 32), ov);
+        tmem_ld_32x32b_x32(t_lane + TM_S + static_cast<uint32_t>(h * 128 + win * 32), ov);
         tmem_ld_wait();
         tc_fence_before();
         mbar_arrive(&o_drained[h]);
-        uint8_t* orow = smem + OFF_QKV + h * 8192 + row * 64;      // O_h overwrites Q_h (S_h has consumed it)
+        uint8_t* orow = smem + OFF_QKV + h * 8192 + row * 64;
 #pragma unroll
         for (int c = 0; c < 4; ++c)
           *reinterpret_cast<uint4*>(orow + ((c ^ sw64) << 4)) = make_uint4(
@@ -440,42 +443,38 @@ swin_attn96_fused_kernel(const __grid_constant__ CUtensorMap tmOut, const Attn96
               pack_bf16(__uint_as_float(ov[8 * c + 2]) * inv, __uint_as_float(ov[8 * c + 3]) * inv),
               pack_bf16(__uint_as_float(ov[8 * c + 4]) * inv, __uint_as_float(ov[8 * c + 5]) * inv),
               pack_bf16(__uint_as_float(ov[8 * c + 6]) * inv, __uint_as_float(ov[8 * c + 7]) * inv));
-        fence_proxy_async_smem();
-        mbar_arrive(&o_smem_full);
       }
+      fence_proxy_async_smem();
+      mbar_arrive(&o_smem_full);
+      if (elected) TRACE(16 + 7 * h);
 
-      // ---- proj accumulator -> + bias -> 32-column slabs -> TMA reduce-add into x_out (which holds the residual rows)
-      if (elected) TRACE(19 + 10 * group);
-      mbar_wait(&proj_full, par, 83);
-      if (elected) TRACE(30 + group);
+      // ---- proj accumulator columns 32 h .. 32 h + 31 -> + bias -> slab (in P_h) -> TMA reduce-add into x_out, which holds
+      //      the residual rows
+      mbar_wait_relaxed(&proj_full, par, 83, 1000);
+      if (elected) TRACE(31);
       tc_fence_after();
-#pragma unroll 1
-      for (int s = group; s < 3; s += 2) {
+      {
         uint32_t v[32];
-        tmem_ld_32x32b_x32(t_lane + TM_PROJ + static_cast<uint32_t>(32 * s), v);
+        tmem_ld_32x32b_x32(t_lane + TM_PROJ + static_cast<uint32_t>(32 * h), v);
         tmem_ld_wait();
-        if (s + 2 >= 3) {                      // last slab of this group: the accumulator may be overwritten
-          tc_fence_before();
-          mbar_arrive(&proj_drained);
-        }
-        const float* bias = s_vec + 288 + 32 * s;
-        if (elected) tma_store_wait_read<0>();
-        named_bar_sync(1 + group, 128);
+        tc_fence_before();
+        mbar_arrive(&proj_drained);
+        const float* bias = s_vec + 288 + 32 * h;
 #pragma unroll
         for (int c = 0; c < 8; ++c) {
           const float4 b4 = *reinterpret_cast<const float4*>(bias + 4 * c);
-          *reinterpret_cast<float4*>(slab + row * 128 + ((c ^ sw128) << 4)) =
+          *reinterpret_cast<float4*>(ptile + row * 128 + ((c ^ sw128) << 4)) =
               make_float4(__uint_as_float(v[4 * c]) + b4.x, __uint_as_float(v[4 * c + 1]) + b4.y,
                           __uint_as_float(v[4 * c + 2]) + b4.z, __uint_as_float(v[4 * c + 3]) + b4.w);
         }
-        fence_proxy_async_smem();
-        named_bar_sync(1 + group, 128);
-        if (elected) {
-          const int row0 = tile * TILE_TOK;
-          tma_reduce_add_f32_2d(&tmOut, slab, 32 * s, row0);                       // window 0: slab rows 0..48
-          tma_reduce_add_f32_2d(&tmOut, slab + 64 * 128, 32 * s, row0 + NTOK);     // window 1: slab rows 64..112
-          tma_store_commit();
-        }
+      }
+      fence_proxy_async_smem();
+      named_bar_sync(1 + h, 128);
+      if (elected) {
+        const int row0 = tile * TILE_TOK;
+        tma_reduce_add_f32_2d(&tmOut, ptile, 32 * h, row0);                       // window 0: slab rows 0..48
+        tma_reduce_add_f32_2d(&tmOut, ptile + 64 * 128, 32 * h, row0 + NTOK);     // window 1: slab rows 64..112
+        tma_store_commit();
       }
     }
     if (elected) tma_store_wait_all();

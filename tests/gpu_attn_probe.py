@@ -41,12 +41,11 @@ for shift in (0, 3):
     run(tr); torch.cuda.synchronize()
     t = tr.cpu().view(8, 32)
     base = t[0, 0].item()
-    names = {0: "mma:start", 1: "mma:a_full", 2: "mma:qkv issued", 3: "mma:qkv_smem_full", 4: "mma:p_full0", 5: "mma:p_full1",
-             6: "mma:p_full2+o_dr0", 7: "mma:o_smem_full", 8: "mma:proj issued",
-             10: "g0:tile start", 11: "g0:qkv_full", 12: "g0:qkv drained", 13: "g0:s_full0", 14: "g0:P0 written", 15: "g0:o_full0",
-             16: "g0:s_full2", 17: "g0:P2 written", 18: "g0:o_full2", 19: "g0:O2 drained", 30: "g0:proj_full",
-             20: "g1:tile start", 21: "g1:qkv_full", 22: "g1:qkv drained", 23: "g1:s_full1", 24: "g1:P1 written", 25: "g1:o_full1",
-             29: "g1:O1 drained", 31: "g1:proj_full"}
+    names = {0: "mma:start", 1: "mma:a_full", 2: "mma:qkv issued", 3: "mma:qkv_ready", 4: "mma:p_full0", 5: "mma:p_full1",
+             6: "mma:p_full2", 7: "mma:o_smem_full", 8: "mma:proj issued", 31: "g:proj_full"}
+    for h in range(3):
+        for k, n in enumerate(["tile start", "qkv_full", "qkv drained", "s_full", "P written", "o_full", "O drained"]):
+            names[10 + 7 * h + k] = f"g{h}:{n}"
     for i in (2, 3):
         ev = sorted((t[i, k].item() - base, names[k]) for k in names if t[i, k].item() != 0)
         print(f"  tile {i}: " + "  ".join(f"{n}@{c}" for c, n in ev))
