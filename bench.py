@@ -153,7 +153,7 @@ def workload_config(args, world):
                         f"({'112x112x3 uint8 crops resized on device' if args.ingest == 'u8' else '3x224x224 fp32'}, synthetic), "
                         f"{args.text_len}-token dialogue text, 160x768 audio, 160x512 vision",
             "global_batch": args.batch * world, "text_len": args.text_len, "frames_per_utterance": 160,
-            "precision": args.precision, "ingest": args.ingest,
+            "precision": args.precision, "ingest": args.ingest, "cuda_graph": bool(args.graph),
             "batch_semantics": "per-utterance filter fallback (== the reference at its default trg_batch_size=1; its U>1 "
                                "re-pack off-by-one, train.py:200,213, is not reproduced)",
             "parallelism": f"utterance sharding x{world} (NCCL all-gather of logits)",
@@ -240,6 +240,9 @@ def run_ours(args):
         mm.load_state_dict(mm_sd)
         del mm_sd
     mods = [m for m in (swin, mm) if m is not None]
+    if args.graph:
+        for m in mods:
+            m.set_graph(True)          # repeated identical steps (same device buffers) replay as one CUDA graph launch
 
     b = make_inputs(cfg, U, L, seed=1111 + 1000 * rank, ingest=args.ingest)
     dev = {k: (v.cuda() if torch.is_tensor(v) else v) for k, v in b.items()}
@@ -495,6 +498,7 @@ def main():
     ap.add_argument("--cpu-baseline-batches", type=int, default=2)
     ap.add_argument("--swin-chunk", type=int, default=0)
     ap.add_argument("--swin-chunk-late", type=int, default=0)
+    ap.add_argument("--graph", type=int, default=1, help="1: replay repeated identical steps as a CUDA graph (fmmt_set_graph)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-parity", action="store_true")
     ap.add_argument("--no-latency", action="store_true")

@@ -62,6 +62,7 @@ SIGNATURES = {
                                               c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p]),
     "fmmt_unimodal_forward": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
     "fmmt_check": (c_int, [c_void_p]),
+    "fmmt_set_graph": (c_int, [c_void_p, c_int]),
     "fmmt_set_capture": (c_int, [c_void_p, c_char_p, c_void_p, c_int64]),
     "fmmt_set_profile": (c_int, [c_void_p, c_int]),
     "fmmt_profile_read": (c_int64, [c_void_p, c_void_p, c_int64]),

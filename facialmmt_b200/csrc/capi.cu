@@ -131,6 +131,12 @@ FMMT_API int fmmt_check(fmmt_handle* h) {
   return h->eng->check();
 }
 
+FMMT_API int fmmt_set_graph(fmmt_handle* h, int enable) {
+  if (!h) return set_error(FMMT_ERR_INVALID, "null handle");
+  h->eng->set_graph(enable != 0);
+  return FMMT_OK;
+}
+
 FMMT_API int fmmt_set_capture(fmmt_handle* h, const char* name, float* dst, int64_t count) {
   if (!h) return set_error(FMMT_ERR_INVALID, "null handle");
   return h->eng->set_capture(name, dst, count);

@@ -158,6 +158,8 @@ class Engine {
   // Per-kernel CUDA-event timing (on the launch stream) for roofline accounting; adds two event records per launch.
   void set_profile(bool on);
   std::string profile_json();  // synchronises; aggregates by kernel key since set_profile(true)
+  // CUDA-graph replay of repeated identical forwards (same pointers / sizes / stream): see Engine::run.
+  void set_graph(bool on);
   // Synchronises the stream of the last forward and reports a pipeline-watchdog event (ptx.cuh) of any forward since
   // the previous check: FMMT_OK or FMMT_ERR_CUDA (message via fmmt_last_error). Clears the condition.
   int check();
@@ -225,7 +227,17 @@ class Engine {
                        const float* audio_mask, const float* vision, const float* vision_mask, const int64_t* idx, int U,
                        int L, float* logits, const int32_t* text_row, int n_text);
   void unimodal_body(const float* inputs, const float* mask, int U, float* logits);
-  template <typename Fn> int run(Fn&& body, cudaStream_t st);
+  template <typename Fn> int run(Fn&& body, cudaStream_t st, const std::vector<unsigned long long>& key);
+  struct GraphEntry {
+    std::vector<unsigned long long> key;
+    cudaGraphExec_t exec = nullptr;
+    int seen = 0;
+    int launches = 0;
+    double flops = 0;
+  };
+  std::unordered_map<unsigned long long, GraphEntry> graphs_;
+  bool graph_on_ = false;
+  void drop_graphs();
 
   fmmt_config cfg_;
   bool precise_ = false;   // fp32-grade mode (cfg.precision == 1)

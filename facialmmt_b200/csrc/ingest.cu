@@ -169,7 +169,7 @@ ingest_im2col_kernel(const uint8_t* __restrict__ crops, const IngestTables t, fl
                      __nv_bfloat16* __restrict__ out_col, int split) {
   extern __shared__ float s_dyn[];
   float* s_img = s_dyn;                                 // [3][4][224]
-  int* s_hor_i = reinterpret_cast<int*>(s_dyn + 12 * DST);     // cubic: [4][4][224*3] int32
+  int* s_hor_i = reinterpret_cast<int*>(s_dyn + 12 * DST);     // cubic: [8 distinct source rows][224*3] int32, then the rows' bytes
   float* s_hor_f = s_dyn + 12 * DST;                    // area : [4][nent][224*3] float
   const int PH = DST / 4;
   const int f = blockIdx.x / PH, py = blockIdx.x - f * PH;
@@ -177,29 +177,39 @@ ingest_im2col_kernel(const uint8_t* __restrict__ crops, const IngestTables t, fl
   const int RW = DST * 3;
 
   if (t.mode == MODE_CUBIC) {
-    for (int idx = threadIdx.x; idx < 16 * RW; idx += blockDim.x) {
-      const int jk = idx / RW, xc3 = idx - jk * RW;
+    // the 4 output rows read source rows yi[4 py][0] .. yi[4 py + 3][3] (monotonic, at most 7 distinct rows when upscaling):
+    // stage them in shared memory once (coalesced), run the horizontal pass once per DISTINCT row, then the vertical pass
+    const int ymin = __ldg(t.yi + (py * 4) * 4), ymax = __ldg(t.yi + (py * 4 + 3) * 4 + 3);
+    const int nrows = ymax - ymin + 1;                          // <= 8 (launch_frame_ingest checks H < 224)
+    const int rowb = t.W * 3;
+    uint8_t* s_src = reinterpret_cast<uint8_t*>(s_hor_i + 8 * RW);   // [8][W * 3] bytes
+    for (int idx = threadIdx.x; idx < nrows * rowb; idx += blockDim.x) {
+      const int r = idx / rowb, b = idx - r * rowb;
+      s_src[r * rowb + b] = src[static_cast<size_t>(ymin + r) * rowb + b];
+    }
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < nrows * RW; idx += blockDim.x) {
+      const int r = idx / RW, xc3 = idx - r * RW;
       const int dx = xc3 / 3, c = xc3 - dx * 3;
-      const int dy = py * 4 + (jk >> 2);
-      const int sy = __ldg(t.yi + dy * 4 + (jk & 3));
-      const uint8_t* row = src + static_cast<size_t>(sy) * t.W * 3 + c;
-      int acc = 0;
-#pragma unroll
-      for (int k = 0; k < 4; ++k) acc += static_cast<int>(row[__ldg(t.xi + dx * 4 + k) * 3]) * __ldg(t.xc + dx * 4 + k);
-      s_hor_i[idx] = acc;
+      const uint8_t* row = s_src + r * rowb + c;
+      const int4 xi4 = __ldg(reinterpret_cast<const int4*>(t.xi) + dx);
+      const int4 xc4 = __ldg(reinterpret_cast<const int4*>(t.xc) + dx);
+      s_hor_i[idx] = static_cast<int>(row[xi4.x * 3]) * xc4.x + static_cast<int>(row[xi4.y * 3]) * xc4.y +
+                     static_cast<int>(row[xi4.z * 3]) * xc4.z + static_cast<int>(row[xi4.w * 3]) * xc4.w;
     }
     __syncthreads();
     for (int idx = threadIdx.x; idx < 4 * RW; idx += blockDim.x) {
       const int j = idx / RW, xc3 = idx - j * RW;
       const int dx = xc3 / 3, c = xc3 - dx * 3;
       const int dy = py * 4 + j;
-      const float b0 = __ldg(t.yb + dy * 4), b1 = __ldg(t.yb + dy * 4 + 1), b2 = __ldg(t.yb + dy * 4 + 2), b3 = __ldg(t.yb + dy * 4 + 3);
-      const float S0 = static_cast<float>(s_hor_i[(j * 4 + 0) * RW + xc3]), S1 = static_cast<float>(s_hor_i[(j * 4 + 1) * RW + xc3]);
-      const float S2 = static_cast<float>(s_hor_i[(j * 4 + 2) * RW + xc3]), S3 = static_cast<float>(s_hor_i[(j * 4 + 3) * RW + xc3]);
-      float r = __fmul_rn(S3, b3);
-      r = __fmaf_rn(S2, b2, r);
-      r = __fmaf_rn(S1, b1, r);
-      r = __fmaf_rn(S0, b0, r);
+      const int4 y4 = __ldg(reinterpret_cast<const int4*>(t.yi) + dy);
+      const float4 b4 = __ldg(reinterpret_cast<const float4*>(t.yb) + dy);
+      const float S0 = static_cast<float>(s_hor_i[(y4.x - ymin) * RW + xc3]), S1 = static_cast<float>(s_hor_i[(y4.y - ymin) * RW + xc3]);
+      const float S2 = static_cast<float>(s_hor_i[(y4.z - ymin) * RW + xc3]), S3 = static_cast<float>(s_hor_i[(y4.w - ymin) * RW + xc3]);
+      float r = __fmul_rn(S3, b4.w);
+      r = __fmaf_rn(S2, b4.z, r);
+      r = __fmaf_rn(S1, b4.y, r);
+      r = __fmaf_rn(S0, b4.x, r);
       int v = __float2int_rn(r);                        // round-half-even
       v = v < 0 ? 0 : (v > 255 ? 255 : v);
       const float x = __fdiv_rn(static_cast<float>(v), 255.0f);           // ToTensor
@@ -293,7 +303,7 @@ cudaError_t launch_frame_ingest(const uint8_t* crops, int F, int H, int W, float
   const IngestTables* t = get_tables(H, W);
   if (t == nullptr) return cudaErrorInvalidValue;
   size_t smem = 12 * DST * sizeof(float);
-  if (t->mode == MODE_CUBIC) smem += 16 * DST * 3 * sizeof(int);
+  if (t->mode == MODE_CUBIC) smem += 8 * DST * 3 * sizeof(int) + static_cast<size_t>(8) * W * 3 + 16;
   if (t->mode == MODE_AREA) smem += static_cast<size_t>(4) * t->nent * DST * 3 * sizeof(float);
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;

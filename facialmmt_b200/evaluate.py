@@ -42,7 +42,8 @@ def evaluate_batch(swin_model, multimodal_model, batch, threshold: float = 0.2, 
     if gumbel is None:      # the draw F.gumbel_softmax makes internally (src/models.py:31-32)
         gumbel = -torch.empty(F, swin_model.num_labels, device="cuda").exponential_().log()
     _, probs, _ = swin_model.forward_full(frames, gumbel)
-    v519, new_mask = filter_pack(vision, vision_mask, n, probs, threshold, per_utterance)
+    cache = swin_model._out_cache if getattr(swin_model, "_graph", False) else None     # graph mode: stable buffers
+    v519, new_mask = filter_pack(vision, vision_mask, n, probs, threshold, per_utterance, cache=cache)
     logits = multimodal_model(ids, mask, sep, audio, audio_mask, v519, new_mask, idx)
     if return_intermediates:
         return logits, dict(probs=probs, vision519=v519, new_mask=new_mask)

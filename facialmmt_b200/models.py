@@ -155,6 +155,24 @@ class _Module:
         self._captures.clear()
         _lib.check(self._lib.fmmt_set_capture(self._h, None, None, 0), "fmmt_set_capture")
 
+    def set_graph(self, on: bool = True):
+        """Replay repeated identical forwards (same tensors / sizes / stream) as one CUDA graph launch (fmmt_set_graph).
+        While on, the module hands out the SAME output tensors for equal shapes (a graph replays fixed pointers): the result
+        of a forward is overwritten by the next forward of the same shape."""
+        _lib.check(self._lib.fmmt_set_graph(self._h, int(on)), "fmmt_set_graph")
+        self._graph = bool(on)
+        self._out_cache = {}
+
+    def _out(self, key, shape):
+        """Output tensor: fresh, or (graph mode) the persistent one for this key/shape."""
+        if not getattr(self, "_graph", False):
+            return torch.empty(*shape, device="cuda", dtype=torch.float32)
+        k = (key, tuple(shape))
+        t = self._out_cache.get(k)
+        if t is None:
+            t = self._out_cache[k] = torch.empty(*shape, device="cuda", dtype=torch.float32)
+        return t
+
     def set_profile(self, on: bool = True):
         _lib.check(self._lib.fmmt_set_profile(self._h, int(on)), "fmmt_set_profile")
 
@@ -245,10 +263,10 @@ class SwinForAffwildClassification(_Module):
         g = _f32(gumbel) if gumbel is not None else None
         if g is not None and tuple(g.shape) != (F, s.num_labels):
             raise ValueError("gumbel noise must have shape (frames, num_labels)")
-        logits = torch.empty(F, s.num_labels, device="cuda", dtype=torch.float32)
-        probs = torch.empty_like(logits)
-        imp = torch.empty(F, device="cuda", dtype=torch.float32)
-        feat = torch.empty(F, s.feat_dim, device="cuda", dtype=torch.float32) if want_feat else None
+        logits = self._out("logits", (F, s.num_labels))
+        probs = self._out("probs", (F, s.num_labels))
+        imp = self._out("imp", (F,))
+        feat = self._out("feat", (F, s.feat_dim)) if want_feat else None
         if u8:
             _lib.check(self._lib.fmmt_swin_forward_u8(self._h, _lib.ptr(x), F, int(x.shape[1]), int(x.shape[2]), _lib.ptr(g),
                                                       float(self.tau), _lib.ptr(logits), _lib.ptr(probs), _lib.ptr(imp),
@@ -344,7 +362,7 @@ class MultiModalTransformerForClassification(_Module):
             raise ValueError(f"vision must be (U,{f.vision_len},{f.vision_dim + f.num_labels}) with mask (U,{f.vision_len})")
         if idx.numel() != U:
             raise ValueError("batchUtt_in_dia_idx must have U entries")
-        logits = torch.empty(U, f.num_labels, device="cuda", dtype=torch.float32)
+        logits = self._out("logits", (U, f.num_labels))
         if row_of_utt is not None:
             _lib.check(self._lib.fmmt_multimodal_forward_dedup(self._h, _lib.ptr(ids), _lib.ptr(msk), Ud, _lib.ptr(row_of_utt),
                                                                _lib.ptr(sep), _lib.ptr(a), _lib.ptr(am), _lib.ptr(v),
@@ -378,7 +396,7 @@ class meld_utt_transformer(_Module):  # noqa: N801  (reference class name)
         U = x.shape[0]
         if tuple(x.shape) != (U, f.vision_len, f.vision_dim) or tuple(m.shape) != (U, f.vision_len):
             raise ValueError(f"inputs must be (U,{f.vision_len},{f.vision_dim}) with utt_mask (U,{f.vision_len})")
-        logits = torch.empty(U, f.num_labels, device="cuda", dtype=torch.float32)
+        logits = self._out("logits", (U, f.num_labels))
         _lib.check(self._lib.fmmt_unimodal_forward(self._h, _lib.ptr(x), _lib.ptr(m), U, _lib.ptr(logits),
                                                    _lib.cur_stream()), "fmmt_unimodal_forward")
         return logits
@@ -400,8 +418,9 @@ def frame_ingest(crops_u8: torch.Tensor) -> torch.Tensor:
 
 
 def filter_pack(vision_inputs: torch.Tensor, vision_mask: torch.Tensor, num_imgs, probs: torch.Tensor,
-                threshold: float = 0.2, per_utterance: bool = True):
-    """Device-side restatement of train.py:183-232 -> (vision519 (U,Lv,D+labels), new_mask (U,Lv))."""
+                threshold: float = 0.2, per_utterance: bool = True, cache: Optional[dict] = None):
+    """Device-side restatement of train.py:183-232 -> (vision519 (U,Lv,D+labels), new_mask (U,Lv)). `cache`: a dict in which
+    the outputs / offsets are kept across calls of equal shape (graph mode: stable pointers for the fusion forward)."""
     _require_cuda()
     lib = _lib.load()
     v, m, p = _f32(vision_inputs), _f32(vision_mask), _f32(probs)
@@ -410,10 +429,16 @@ def filter_pack(vision_inputs: torch.Tensor, vision_mask: torch.Tensor, num_imgs
     n = [int(x) for x in (num_imgs.tolist() if torch.is_tensor(num_imgs) else num_imgs)]
     if len(n) != U or sum(n) != p.shape[0] or any(x < 0 or x > Lv for x in n):
         raise ValueError("num_imgs must have one entry per utterance, each <= Lv, summing to probs.shape[0]")
-    off = torch.tensor([0] + list(torch.tensor(n).cumsum(0).tolist()), dtype=torch.int32).to("cuda", non_blocking=True)
-    out_v = torch.empty(U, Lv, D + labels, device="cuda", dtype=torch.float32)
-    out_m = torch.empty(U, Lv, device="cuda", dtype=torch.float32)
-    scratch = torch.zeros(1, device="cuda", dtype=torch.int32)
+    ck = ("filter_pack", U, Lv, D, labels, tuple(n))
+    if cache is not None and ck in cache:
+        off, out_v, out_m, scratch = cache[ck]
+    else:
+        off = torch.tensor([0] + list(torch.tensor(n).cumsum(0).tolist()), dtype=torch.int32).to("cuda", non_blocking=True)
+        out_v = torch.empty(U, Lv, D + labels, device="cuda", dtype=torch.float32)
+        out_m = torch.empty(U, Lv, device="cuda", dtype=torch.float32)
+        scratch = torch.zeros(1, device="cuda", dtype=torch.int32)
+        if cache is not None:
+            cache[ck] = (off, out_v, out_m, scratch)
     _lib.check(lib.fmmt_filter_pack(_lib.ptr(v), _lib.ptr(m), _lib.ptr(off), p.shape[0], _lib.ptr(p), float(threshold),
                                     int(per_utterance), _lib.ptr(out_v), _lib.ptr(out_m), _lib.ptr(scratch), U, Lv, D,
                                     labels, _lib.cur_stream()), "fmmt_filter_pack")

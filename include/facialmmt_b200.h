@@ -151,6 +151,13 @@ FMMT_API int fmmt_unimodal_forward(fmmt_handle* h, const float* inputs, const fl
  * logits (evaluate.py, bench.py and smoke() do). */
 FMMT_API int fmmt_check(fmmt_handle* h);
 
+/* CUDA-graph replay (off by default). When enabled, the second forward of a handle with IDENTICAL arguments (same pointers,
+ * sizes, scalars and stream) is captured into a CUDA graph and every later identical call replays it with a single launch
+ * (results are the same kernels on the same buffers; the data the pointers hold may change between calls). Meant for
+ * steady-state loops over pre-allocated buffers, e.g. the reference's default trg_batch_size = 1 eval loop (main.py:56),
+ * which is launch-bound. Captures / profiling bypass the graph; at most 16 argument sets are cached per handle. */
+FMMT_API int fmmt_set_graph(fmmt_handle* h, int enable);
+
 /* Stage-wise parity hook: during the next forwards, copy the named fp32 intermediate into `dst` (device, `count`
  * floats). name == NULL clears all captures. Names: swin.patch_embed, swin.layer<l>.block<b>, swin.feat,
  * mm.text768, mm.text, mm.audio, mm.vision, mm.ta, mm.fused. */
