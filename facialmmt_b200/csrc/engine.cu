@@ -37,6 +37,7 @@ Engine::~Engine() {
   for (auto& r : prof_recs_) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
   for (cudaEvent_t e : ev_pool_) cudaEventDestroy(e);
   drop_graphs();
+  if (graph_stream_) cudaStreamDestroy(graph_stream_);
   for (void* p : dev_ptrs_) cudaFree(p);
   if (ws_) cudaFree(ws_);
   if (status_host_) cudaFreeHost(status_host_);
@@ -854,7 +855,12 @@ int Engine::run(Fn&& body, cudaStream_t st, const std::vector<unsigned long long
   const long long launches0 = launch_count();
   const double flops0 = flops_;
   if (capture) {
-    cudaError_t e = cudaStreamBeginCapture(st, cudaStreamCaptureModeRelaxed);
+    // captured on a private stream (the caller's may be the legacy default stream, which cannot be captured); the
+    // instantiated graph is then launched into the caller's stream
+    if (graph_stream_ == nullptr && cudaStreamCreateWithFlags(&graph_stream_, cudaStreamNonBlocking) != cudaSuccess)
+      return set_error(FMMT_ERR_CUDA, "cudaStreamCreate (graph capture stream) failed");
+    st_ = graph_stream_;
+    cudaError_t e = cudaStreamBeginCapture(graph_stream_, cudaStreamCaptureModeRelaxed);
     if (e != cudaSuccess) return set_error(FMMT_ERR_CUDA, std::string("cudaStreamBeginCapture: ") + cudaGetErrorString(e));
   }
   arena_.begin(false, ws_, ws_cap_);
@@ -869,7 +875,8 @@ int Engine::run(Fn&& body, cudaStream_t st, const std::vector<unsigned long long
   }
   if (capture) {
     cudaGraph_t g = nullptr;
-    cudaError_t e = cudaStreamEndCapture(st, &g);
+    cudaError_t e = cudaStreamEndCapture(graph_stream_, &g);
+    st_ = st;
     if (e != cudaSuccess || g == nullptr || first_err_ != cudaSuccess) {
       if (g) cudaGraphDestroy(g);
       cudaGetLastError();

@@ -237,6 +237,7 @@ class Engine {
   };
   std::unordered_map<unsigned long long, GraphEntry> graphs_;
   bool graph_on_ = false;
+  cudaStream_t graph_stream_ = nullptr;   // private capture stream
   void drop_graphs();
 
   fmmt_config cfg_;
