@@ -82,7 +82,7 @@ def _make_stub_pickle_module():
     import pickle
     import types
 
-    safe_roots = ("torch", "collections", "builtins", "numpy", "_codecs", "copyreg")
+    safe_roots = ("torch", "collections", "builtins", "__builtin__", "numpy", "_codecs", "copyreg", "copy_reg")
 
     class StubUnpickler(pickle.Unpickler):
         def find_class(self, module, name):

@@ -49,6 +49,9 @@ def build_parser():
     p.add_argument("--precision", type=str, default="bf16", choices=["bf16", "fp32"],
                    help="bf16: bf16 operands / fp32 accumulate (logits within 1e-2 of the fp32 reference); fp32: split-bf16 x3 "
                         "operands + fp32 attention (within 1e-3)")
+    p.add_argument("--bug_compat", type=int, default=0,
+                   help="1: reproduce the reference's literal batch re-pack at trg_batch_size > 1, off-by-one included "
+                        "(train.py:200,213); default 0 = per-utterance semantics (== the reference at trg_batch_size 1)")
     p.add_argument("--trust_checkpoint", type=int, default=0,
                    help="allow unpickling the reference's whole-module checkpoints (train.py:428-432); executes pickle code")
     return p
@@ -67,6 +70,9 @@ def main(argv=None):
     _TRUST["on"] = bool(args.trust_checkpoint)
     if not args.doEval:
         raise SystemExit("facialmmt_b200 implements --doEval (inference) only")
+    if args.trg_batch_size > 1 and not args.bug_compat:
+        print(f"[facialmmt_b200] trg_batch_size={args.trg_batch_size}: utterances are evaluated with the reference's batch-size-1 "
+              "semantics (its literal U>1 re-pack drops/shifts frames: train.py:200,213). Pass --bug_compat 1 for the literal code.")
     import torch.distributed as dist
     from facialmmt_b200 import synthetic as syn
     from facialmmt_b200.config import FmmtConfig, FusionConfig, TextConfig
@@ -113,7 +119,7 @@ def main(argv=None):
             batch = (b["text_ids"], b["text_mask"], b["sep_mask"], b["audio"], b["audio_mask"], b["vision"],
                      b["vision_mask"], labels[u0:u1], b["faces"], b["num_imgs"], b["idx_in_dia"])
             results.append(evaluate_batch(swin, mm, batch, args.FacialEmoImpor_threshold,
-                                          per_utterance=bool(args.per_utterance)))
+                                          per_utterance=bool(args.per_utterance), bug_compat=bool(args.bug_compat)))
     local = torch.cat(results) if results else torch.zeros(0, args.num_labels, device="cuda")
     logits = gather_logits(local, n)
     if rank == 0:

@@ -131,3 +131,69 @@ def test_checkpoint_ingestion_wrappers_and_backbone_remap(tmp_path):
             k_val = k[5:] if k[:5] == 'swin.' else k
             ref[k] = pre['backbone.' + k_val]
     assert set(remap_pretrained_backbone(model_keys, pre, literal=True)) == set(ref) == {"linear.weight"}
+
+
+def test_pickled_lite_module_checkpoint_loads_without_lightning(tmp_path):
+    """train.py:428-432 loads whole pickled `_LiteModule(DataParallel(module))` objects (utils/util.py:121-132 saves them after
+    Lite.setup). checkpoint.load_state_dict_file must (a) refuse to unpickle them unless trusted, (b) read them WITHOUT
+    pytorch_lightning or the reference's classes importable, giving the reference's own key names."""
+    import sys
+    import types
+
+    import torch.nn as nn
+    from facialmmt_b200 import checkpoint as ck
+
+    pl = types.ModuleType("pytorch_lightning"); lite = types.ModuleType("pytorch_lightning.lite")
+    wr = types.ModuleType("pytorch_lightning.lite.wrappers"); refmod = types.ModuleType("src_models_fake")
+
+    class _LiteModule(nn.Module):
+        def __init__(self, m):
+            super().__init__()
+            self._forward_module = m
+            self._original_module = m
+
+    class Inner(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.linear = nn.Linear(4, 3)
+            self.bn = nn.BatchNorm1d(3)
+            self.register_buffer("pos", torch.arange(5.0))
+
+    _LiteModule.__module__ = "pytorch_lightning.lite.wrappers"; _LiteModule.__qualname__ = "_LiteModule"
+    Inner.__module__ = "src_models_fake"; Inner.__qualname__ = "Inner"
+    wr._LiteModule = _LiteModule; refmod.Inner = Inner
+    names = {"pytorch_lightning": pl, "pytorch_lightning.lite": lite, "pytorch_lightning.lite.wrappers": wr,
+             "src_models_fake": refmod}
+    sys.modules.update(names)
+    try:
+        inner = Inner()
+        obj = _LiteModule(nn.DataParallel(inner))
+        path = str(tmp_path / "multimodal_fake.pt")
+        torch.save(obj, path)
+        want = {k: v.clone() for k, v in inner.state_dict().items()}
+    finally:
+        for k in names:
+            sys.modules.pop(k, None)
+    with pytest.raises(RuntimeError, match="trust_checkpoint"):
+        ck.load_state_dict_file(path)                       # default: no code execution
+    got = ck.load_state_dict_file(path, trust=True)         # neither Lightning nor the model class is importable now
+    assert set(got) == set(want), (sorted(got), sorted(want))
+    for k in want:
+        assert torch.equal(got[k], want[k]), k
+    # a plain state_dict file needs no trust
+    p2 = str(tmp_path / "sd.pt")
+    torch.save({"module." + k: v for k, v in want.items()}, p2)
+    got2 = ck.load_state_dict_file(p2)
+    assert set(got2) == set(want)
+
+
+def test_literal_batch_repack_reproduces_the_reference_bug():
+    """SURVEY F7 toy batch n = [4, 3, 5], every frame kept: utterance 1 receives 2 of its 3 frames with local indices
+    shifted by +1, utterance 2 is shifted by +2, 10 of 12 frames are consumed (train.py:192-213)."""
+    from facialmmt_b200.evaluate import literal_batch_repack
+    counts, prob_row, vision_row = literal_batch_repack([4, 3, 5], list(range(12)), Lv=160)
+    assert counts == [4, 2, 4]
+    assert prob_row == [[0, 1, 2, 3], [4, 5], [6, 7, 8, 9]]
+    assert vision_row == [[0, 1, 2, 3], [1, 2], [1, 2, 3, 4]]
+    # batch size 1 is exact
+    assert literal_batch_repack([5], [0, 2, 4], 160) == ([3], [[0, 2, 4]], [[0, 2, 4]])

@@ -60,3 +60,39 @@ def test_multimodal_keys_and_cmt_module():
         ref = mm.CrossModalTrans_TA(q.transpose(0, 1), kv.transpose(0, 1), kv.transpose(0, 1)).transpose(0, 1)
     got = orc.cmt_encoder(sd, "CrossModalTrans_TA.", q, kv)
     assert (ref - got).abs().max() < 2e-4
+
+
+def test_bug_compat_repack_equals_the_literal_reference_loop_at_batch_3():
+    """--bug_compat: facialmmt_b200.evaluate._filter_pack_bug_compat against the reference's OWN multimodal_evaluate loop
+    (train.py:154-243, exec'd from source) at trg_batch_size = 3, where the literal code drops / shifts frames."""
+    import argparse
+
+    from facialmmt_b200 import synthetic as syn
+    from facialmmt_b200.config import FmmtConfig
+    from facialmmt_b200.evaluate import _filter_pack_bug_compat
+    rh.install_shims()
+    cfg = FmmtConfig()
+    n = [37, 5, 160]
+    b = syn.synthetic_batch(cfg, U=3, L=16, seed=77, n_frames=n, with_faces=False)
+    for sharp in (2.0, 0.0):
+        probs = torch.softmax(sharp * torch.randn(sum(n), 7, generator=torch.Generator().manual_seed(9)), -1)
+
+        class Swin(torch.nn.Module):
+            def forward(self, x, is_trg_task=None):
+                return probs
+
+        class Cap(torch.nn.Module):
+            def forward(self, *a):
+                self.got = [t.clone() for t in a]
+                return torch.zeros(a[5].shape[0], 7)
+
+        cap = Cap()
+        args = argparse.Namespace(trg_batch_size=3, FacialEmoImpor_threshold=0.2, num_labels=7, trg_n_test=3, trg_n_valid=3)
+        faces = torch.zeros(3, 160, 3, 2, 2)
+        batch = (b["text_ids"], b["text_mask"], b["sep_mask"], b["audio"], b["audio_mask"], b["vision"], b["vision_mask"],
+                 torch.zeros(3, dtype=torch.long), faces, b["num_imgs"], b["idx_in_dia"])
+        with torch.no_grad():
+            rh.literal_eval_loop()(args, [batch])(Swin(), cap, lambda lo, y: torch.zeros(()), test=True)
+        v519, mask = _filter_pack_bug_compat(b["vision"], b["vision_mask"], n, probs, 0.2)
+        assert torch.equal(cap.got[5], v519), sharp
+        assert torch.equal(cap.got[6].float(), mask), sharp
