@@ -49,6 +49,13 @@ def build_parser():
     p.add_argument("--precision", type=str, default="bf16", choices=["bf16", "fp32"],
                    help="bf16: bf16 operands / fp32 accumulate (logits within 1e-2 of the fp32 reference); fp32: split-bf16 x3 "
                         "operands + fp32 attention (within 1e-3)")
+    p.add_argument("--dialogues", type=str, default="",
+                   help="JSON [{'utterances': [text | [token ids], ...]}, ...]: evaluate every utterance with its dialogue encoded "
+                        "as src/meld_bert_extraText.py does (facialmmt_b200.text_frontend); identical dialogues of a batch are "
+                        "encoded once")
+    p.add_argument("--features", type=str, default="", help="torch file with the per-utterance audio/vision/face tensors "
+                                                            "(facialmmt_b200/data.py); synthetic stand-ins when absent")
+    p.add_argument("--tokenizer_path", type=str, default="", help="HF tokenizer directory for string utterances")
     p.add_argument("--bug_compat", type=int, default=0,
                    help="1: reproduce the reference's literal batch re-pack at trg_batch_size > 1, off-by-one included "
                         "(train.py:200,213); default 0 = per-utterance semantics (== the reference at trg_batch_size 1)")
@@ -113,7 +120,27 @@ def main(argv=None):
         mm = MultiModalTransformerForClassification(cfg, precision=args.precision)
         mm.load_state_dict(_load_sd(args.load_multimodal_path) if args.load_multimodal_path
                            else syn.multimodal_stress_state_dict(cfg, args.seed))
-        for u0 in range(lo, hi, args.trg_batch_size):
+        if args.dialogues:
+            # real text path: dialogue-level encoding + per-utterance features (or synthetic stand-ins)
+            from facialmmt_b200 import data as fdata
+            tok = None
+            if args.tokenizer_path:
+                from transformers import AutoTokenizer
+                tok = AutoTokenizer.from_pretrained(args.tokenizer_path)
+            ids, msk, sep, idx = fdata.encode_all(fdata.load_dialogues(args.dialogues), cfg.text.kind, tok)
+            n = len(ids)
+            lo, hi = shard_range(n, rank, world)
+            feats = fdata.load_features(args.features, cfg, n, args.seed)
+            labels = feats["labels"]
+            sl = lambda x: x[lo:hi]   # noqa: E731
+            shard = {k: sl(v) for k, v in feats.items()}
+            for batch in fdata.iter_batches(ids[lo:hi], msk[lo:hi], sep[lo:hi], idx[lo:hi], shard, args.trg_batch_size):
+                results.append(evaluate_batch(swin, mm, batch, args.FacialEmoImpor_threshold,
+                                              per_utterance=bool(args.per_utterance), bug_compat=bool(args.bug_compat)))
+            u_range = range(0)
+        else:
+            u_range = range(lo, hi, args.trg_batch_size)
+        for u0 in u_range:
             u1 = min(hi, u0 + args.trg_batch_size)
             b = syn.synthetic_batch(cfg, U=u1 - u0, L=args.text_len, seed=args.seed + u0, with_faces=True)
             batch = (b["text_ids"], b["text_mask"], b["sep_mask"], b["audio"], b["audio_mask"], b["vision"],

@@ -83,3 +83,29 @@ def test_truncate_live_against_reference_random():
         toks = [[rng.randint(0, 99) for _ in range(rng.choice([0, 1, 2, 5, 5, 9, 30]))] for _ in range(rng.randint(1, 10))]
         mx = rng.choice([0, 3, 10, 25, 200])
         assert tf.truncate_longest_first(toks, mx) == ref._truncate_seq_pair([list(t) for t in toks], mx)
+
+
+def test_data_batches_follow_the_reference_tuple_and_share_dialogue_rows(tmp_path):
+    """facialmmt_b200/data.py: dialogue JSON -> one sample per utterance, dialogue-level ids repeated per utterance (what the
+    model forward de-duplicates), idx_in_dia = position, reference tuple order (utils/dataset.py:291-292)."""
+    import json
+
+    import torch
+    from facialmmt_b200 import data as fdata
+    from facialmmt_b200 import text_frontend as tf
+    from facialmmt_b200.config import FmmtConfig
+    dialogues = [{"utterances": [[11, 12, 13], [21, 22], [31]]}, {"utterances": [[41, 42, 43, 44]]}]
+    path = tmp_path / "d.json"
+    path.write_text(json.dumps(dialogues))
+    ids, mask, sep, idx = fdata.encode_all(fdata.load_dialogues(str(path)), "roberta")
+    assert idx == [0, 1, 2, 0] and len(ids) == 4
+    assert ids[0] == ids[1] == ids[2] and ids[0] != ids[3]
+    assert ids[0][:11] == [0, 11, 12, 13, 2, 2, 21, 22, 2, 2, 31]                 # <s> A </s></s> B </s></s> C </s>
+    assert tf.utterance_spans(sep[0], "roberta") == [(1, 3), (6, 2), (10, 1)]
+    cfg = FmmtConfig()
+    feats = fdata.load_features("", cfg, 4, seed=1)
+    batches = list(fdata.iter_batches(ids, mask, sep, idx, feats, batch_size=3))
+    assert [b[0].shape[0] for b in batches] == [3, 1]
+    b0 = batches[0]
+    assert b0[0].shape == (3, 512) and b0[8].dtype == torch.uint8 and b0[8].shape[1:] == (160, 112, 112, 3)
+    assert b0[10].tolist() == [0, 1, 2] and len(b0[9]) == 3
