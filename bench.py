@@ -259,10 +259,15 @@ def run_ours(args):
                  d["vision_mask"], labels, d["faces"], n_imgs, d["idx_in_dia"])
         return evaluate_batch(swin, mm, batch, cfg.threshold, gumbel=d["gumbel"])
 
+    step_marks = []        # (event after the rank-local compute, event after the all-gather) per timed step, N > 1 only
+
     def step_device():
         out = forward(dev)
         if world > 1 and not swin_only:
+            ev_c = torch.cuda.Event(enable_timing=True); ev_c.record()
             dist.all_gather_into_tensor(gathered, out)
+            ev_g = torch.cuda.Event(enable_timing=True); ev_g.record()
+            step_marks.append((ev_c, ev_g))
             return gathered
         return out
 
@@ -315,12 +320,14 @@ def run_ours(args):
         torch.cuda.synchronize()
         n0 = int(lib.fmmt_launch_count())
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        del step_marks[:]
         e0.record()
         for _ in range(steps):
             fn()
         e1.record()
         torch.cuda.synchronize()
         n1 = int(lib.fmmt_launch_count())
+        timed.e0 = e0
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
@@ -336,6 +343,22 @@ def run_ours(args):
         sampler.start()
     total_ms, gpu_launches = timed(step_device, args.steps, args.warmup)
     clocks = sampler.stop() if rank == 0 else None
+    # per-rank attribution of the scaling loss (N > 1): own compute time per step vs time spent inside the all-gather
+    # waiting for the slowest rank
+    rank_detail = None
+    if world > 1 and step_marks:
+        prev, comp, wait = timed.e0, [], []
+        for ev_c, ev_g in step_marks:
+            comp.append(prev.elapsed_time(ev_c)); wait.append(ev_c.elapsed_time(ev_g)); prev = ev_g
+        mine = torch.tensor([statistics.median(comp), max(comp), statistics.median(wait), max(wait)], device="cuda")
+        allr = torch.empty(world * 4, device="cuda")
+        dist.all_gather_into_tensor(allr, mine)
+        a = allr.view(world, 4).cpu().tolist()
+        rank_detail = {"per_rank_compute_ms_median": [round(r[0], 3) for r in a], "per_rank_compute_ms_max": [round(r[1], 3) for r in a],
+                       "per_rank_allgather_wait_ms_median": [round(r[2], 3) for r in a],
+                       "per_rank_allgather_wait_ms_max": [round(r[3], 3) for r in a],
+                       "note": "compute = previous all-gather end -> this step's logits ready; wait = inside the NCCL all-gather "
+                               "(28 B/utterance: pure wait for the slowest rank of the step)"}
     e2e_steps = max(2, args.steps // 2)
     e2e_ms = float("nan")
     if not args.no_e2e:
@@ -453,6 +476,7 @@ def run_ours(args):
             "clocks": clocks,
             "roofline": roof,
             "path_tensor_frac": value / world * flop_per_utt(args) / (pk["tf_sustained"] * 1e12),
+            "scaling_detail": rank_detail,
             "parity_checked": bool(parity and parity.get("ok")), "parity": parity,
             "latency_u1": lat,
         }

@@ -159,8 +159,8 @@ FMMT_API int64_t fmmt_profile_read(fmmt_handle* h, char* buf, int64_t buf_len) {
 }
 
 FMMT_API uint32_t fmmt_debug_timeout(int reset) {
-  unsigned int* addrs[5] = {watchdog_addr_gemm(), watchdog_addr_mlp96(), watchdog_addr_mlp_stream(), watchdog_addr_attn(),
-                            watchdog_addr_attn96()};
+  unsigned int* addrs[6] = {watchdog_addr_gemm(), watchdog_addr_mlp96(), watchdog_addr_mlp_stream(), watchdog_addr_attn(),
+                            watchdog_addr_attn96(), watchdog_addr_ln_qkv()};
   cudaDeviceSynchronize();
   uint32_t first = 0;
   for (unsigned int* a : addrs) {

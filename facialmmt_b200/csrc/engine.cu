@@ -867,10 +867,10 @@ int Engine::run(Fn&& body, cudaStream_t st, const std::vector<unsigned long long
   body();
   {
     // pipeline watchdog hand-off: collect + clear the per-translation-unit words, copy to the pinned status word
-    unsigned int* addrs[5] = {watchdog_addr_gemm(), watchdog_addr_mlp96(), watchdog_addr_mlp_stream(), watchdog_addr_attn(),
-                              watchdog_addr_attn96()};
+    unsigned int* addrs[6] = {watchdog_addr_gemm(), watchdog_addr_mlp96(), watchdog_addr_mlp_stream(), watchdog_addr_attn(),
+                              watchdog_addr_attn96(), watchdog_addr_ln_qkv()};
     count_launch();
-    ck(launch_collect_status(addrs, 5, status_dev_, st_), "collect_status");
+    ck(launch_collect_status(addrs, 6, status_dev_, st_), "collect_status");
     ck(cudaMemcpyAsync(status_host_, status_dev_, sizeof(unsigned int), cudaMemcpyDeviceToHost, st_), "status copy");
   }
   if (capture) {
@@ -926,6 +926,27 @@ void Engine::swin_block(const SwinStageW& sw, const SwinBlockW& bw, float*& x, f
     if (bw.identity) attn96(x, x, M, sw, bw);
     else { attn96(x, xalt, M, sw, bw); std::swap(x, xalt); }
   } else {
+  static const bool no_ln_qkv = std::getenv("FMMT_NO_LN_QKV") != nullptr;
+  const bool fuse_ln_qkv = !precise_ && !no_ln_qkv && ln_qkv_supported(C, bw.qkv.N) && bw.qkv.b != nullptr && bw.qkv.ld == C;
+  if (fuse_ln_qkv) {
+    // stages 2-3: norm1 + roll + window_partition + qkv Linear in ONE kernel (ln_qkv.cu)
+    if (!arena_.dry() && first_err_ == cudaSuccess) {
+      flops_ += 2.0 * M * static_cast<double>(bw.qkv.N) * C;
+      count_launch();
+      cudaEvent_t e1 = nullptr;
+      if (prof_) e1 = prof_begin("ln_qkv C=" + std::to_string(C) + " M=" + std::to_string(M), 2.0 * M * static_cast<double>(bw.qkv.N) * C,
+                                 (bw.identity ? 4.0 : 8.0) * M * C + 2.0 * M * bw.qkv.N + 2.0 * bw.qkv.N * C);
+      LnQkvArgs a;
+      a.x = x; a.x_raw = bw.identity ? nullptr : xalt; a.M = M; a.C = C; a.T = T;
+      a.gather = bw.identity ? nullptr : bw.gather;
+      a.gamma = bw.ln1.g; a.beta = bw.ln1.b; a.eps = 1e-5f;
+      a.w = bw.qkv.w; a.ldw = bw.qkv.ld; a.bias = bw.qkv.b; a.N = bw.qkv.N;
+      a.out = static_cast<bf16*>(qkv); a.ldo = bw.qkv.N;
+      ck(launch_ln_qkv(a, st_), "ln_qkv");
+      if (prof_) prof_end(e1);
+    }
+    if (!bw.identity) std::swap(x, xalt);
+  } else {
   LnArgs l1;
   l1.in = x; l1.ld_in = C; l1.M = M; l1.nseg = 1; l1.cseg = C;
   l1.gamma = bw.ln1.g; l1.beta = bw.ln1.b; l1.eps = 1e-5f;
@@ -938,6 +959,7 @@ void Engine::swin_block(const SwinStageW& sw, const SwinBlockW& bw, float*& x, f
   ln(l1);
   if (!bw.identity) std::swap(x, xalt);
   lin_to_attn(h, C, M, bw.qkv, qkv);                                 // qkv Linear
+  }
   if (!arena_.dry() && first_err_ == cudaSuccess) {
     count_launch();
     flops_ += 4.0 * M * sw.N * C;

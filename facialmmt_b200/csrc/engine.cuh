@@ -12,6 +12,7 @@
 #include "facialmmt_b200.h"
 #include "attn_fused.cuh"
 #include "gemm.cuh"
+#include "ln_qkv.cuh"
 #include "mlp_fused.cuh"
 #include "mlp_stream.cuh"
 #include "ops.cuh"
