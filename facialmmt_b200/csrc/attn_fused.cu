@@ -235,31 +235,42 @@ swin_attn96_fused_kernel(const __grid_constant__ CUtensorMap tmOut, const Attn96
     const int tt = t >> 3;
     const int rg = 8 * (tt >> 3) + ((tt & 1) << 2) + ((tt >> 1) & 3);   // rows rg + 32 q: swizzle phases spread over the banks
     const bool copy_raw = p.x_out != p.x;
+    auto src_row = [&](int row) -> int {   // composed roll + window_partition gather (within a frame of T tokens)
+      if (p.gather == nullptr) return row;
+      const int fr = row / p.T;
+      return fr * p.T + __ldg(p.gather + (row - fr * p.T));
+    };
     for (int i = 0; i < n_local; ++i) {
       const int tile = static_cast<int>(blockIdx.x) + i * static_cast<int>(gridDim.x);
       float4 xv[4][3];
       bool valid[4];
+      int grow[4], src[4];
+      // every load of the four rows is issued before the first store (x and x_out may alias as far as the compiler knows;
+      // a store between two rows' loads serialises their HBM round trips)
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
         const int r = rg + 32 * q;
         const int tok = r & 63;
         valid[q] = tok < NTOK;
-        if (valid[q]) {
-          const long long grow = static_cast<long long>(tile) * TILE_TOK + (r >> 6) * NTOK + tok;   // row in window order
-          long long src = grow;
-          if (p.gather != nullptr) {
-            const long long fr = grow / p.T;
-            src = fr * p.T + __ldg(p.gather + static_cast<int>(grow - fr * p.T));
+        grow[q] = tile * TILE_TOK + (r >> 6) * NTOK + tok;   // row in window order
+        src[q] = valid[q] ? src_row(grow[q]) : 0;
+      }
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+#pragma unroll
+        for (int j = 0; j < 3; ++j)
+          xv[q][j] = valid[q] ? __ldcg(reinterpret_cast<const float4*>(p.x + static_cast<size_t>(src[q]) * C + 4 * l8 + 32 * j))
+                              : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+      if (i + 1 < n_local && t < TILE_TOK)   // pull the next tile's rows towards L2 (one 384-byte row per thread)
+        prefetch_l2_bulk(p.x + static_cast<size_t>(src_row((tile + static_cast<int>(gridDim.x)) * TILE_TOK + t)) * C, C * 4);
+      if (copy_raw) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          if (valid[q]) {
+#pragma unroll
+            for (int j = 0; j < 3; ++j) *reinterpret_cast<float4*>(p.x_out + static_cast<size_t>(grow[q]) * C + 4 * l8 + 32 * j) = xv[q][j];
           }
-#pragma unroll
-          for (int j = 0; j < 3; ++j) xv[q][j] = __ldcg(reinterpret_cast<const float4*>(p.x + src * C + 4 * l8 + 32 * j));
-          if (copy_raw) {
-#pragma unroll
-            for (int j = 0; j < 3; ++j) *reinterpret_cast<float4*>(p.x_out + grow * C + 4 * l8 + 32 * j) = xv[q][j];
-          }
-        } else {
-#pragma unroll
-          for (int j = 0; j < 3; ++j) xv[q][j] = make_float4(0.f, 0.f, 0.f, 0.f);
         }
       }
       float rstd[4];

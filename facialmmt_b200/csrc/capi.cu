@@ -226,6 +226,19 @@ FMMT_API int fmmt_op_gemm(const void* A_bf16, int lda, const void* W_bf16, int l
   return check_cuda(launch_gemm(a, S(stream)), "fmmt_op_gemm");
 }
 
+FMMT_API int fmmt_op_gemm_ln(const void* A_bf16, int lda, const void* W_bf16, int ldw, int M, int N, int K, const float* bias,
+                             const float* gamma, const float* beta, float eps, float* out_f32, int ldo, void* stream) {
+  if (!A_bf16 || !W_bf16 || !gamma || !beta || !out_f32) return set_error(FMMT_ERR_INVALID, "fmmt_op_gemm_ln: null pointer");
+  GemmArgs a;
+  a.A = static_cast<const __nv_bfloat16*>(A_bf16); a.lda = lda;
+  a.W = static_cast<const __nv_bfloat16*>(W_bf16); a.ldw = ldw;
+  a.M = M; a.N = N; a.K = K; a.bias = bias;
+  a.ln_gamma = gamma; a.ln_beta = beta; a.ln_eps = eps;
+  a.out_f32 = out_f32; a.ldo32 = ldo;
+  count_launch();
+  return check_cuda(launch_gemm(a, S(stream)), "fmmt_op_gemm_ln");
+}
+
 FMMT_API int fmmt_op_layernorm(const float* in, int ld_in, int M, int nseg, int cseg, const int* map, int map_period,
                                int src_period, const float* gamma, const float* beta, float eps, float* out_f32,
                                int ld32, void* out_bf16, int ld16, void* stream) {
@@ -299,6 +312,21 @@ FMMT_API int fmmt_op_swin_mlp_stream(float* x, int M, int C, const float* gamma,
   if (copies < 0) { a.trace = static_cast<long long*>(stream); count_launch(); return check_cuda(launch_mlp_stream(a, nullptr), "fmmt_op_swin_mlp_stream"); }
   count_launch();
   return check_cuda(launch_mlp_stream(a, S(stream)), "fmmt_op_swin_mlp_stream");
+}
+
+FMMT_API int fmmt_op_ln_qkv(const float* x, float* x_raw, int M, int C, int T, const int* gather, const float* gamma,
+                            const float* beta, float eps, const void* w_bf16, int ldw, const float* bias, int N,
+                            void* out_bf16, int ldo, int flags, void* stream) {
+  if (!x || !gamma || !beta || !w_bf16 || !bias || !out_bf16) return set_error(FMMT_ERR_INVALID, "fmmt_op_ln_qkv: null pointer");
+  LnQkvArgs a;
+  a.x = x; a.x_raw = x_raw; a.M = M; a.C = C; a.T = T; a.gather = gather; a.gamma = gamma; a.beta = beta; a.eps = eps;
+  a.w = static_cast<const __nv_bfloat16*>(w_bf16); a.ldw = ldw; a.bias = bias; a.N = N;
+  a.out = static_cast<__nv_bfloat16*>(out_bf16); a.ldo = ldo;
+  count_launch();
+  a.dbg = (flags >> 1) & 3;
+  // debug hook: flags & 1 -> `stream` carries a device trace buffer [8][32] of clock64 stamps (default stream is used)
+  if (flags & 1) { a.trace = static_cast<long long*>(stream); return check_cuda(launch_ln_qkv(a, nullptr), "fmmt_op_ln_qkv"); }
+  return check_cuda(launch_ln_qkv(a, S(stream)), "fmmt_op_ln_qkv");
 }
 
 FMMT_API int fmmt_op_window_attention(const void* qkv_bf16, void* out_bf16, const float* bias, const int8_t* rid,

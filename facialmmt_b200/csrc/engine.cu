@@ -1022,12 +1022,19 @@ void Engine::swin_early(const FrameSrc& frames, int f0, int nf, float* x_out) {
     OP(launch_patch_im2col(frames.f32 + static_cast<size_t>(f0) * frame_elems, col, nf, c.img_size, c.img_size, precise_, st_), "im2col");
   GemmArgs g;
   g.out_f32 = x; g.ldo32 = C0;
+  static const bool no_gemm_ln = std::getenv("FMMT_NO_GEMM_LN") != nullptr;
+  const bool fuse_ln = !no_gemm_ln && C0 <= 256 && (C0 % 32) == 0;
+  if (fuse_ln) {   // PatchEmbed.norm runs in the GEMM epilogue (a thread owns a whole 96-column row)
+    g.ln_gamma = swin_.patch_ln.g; g.ln_beta = swin_.patch_ln.b; g.ln_eps = 1e-5f;
+  }
   gemm_lin(col, 48, M, swin_.patch, g);                              // Conv2d(3,96,k4,s4) as GEMM (K = 48)
-  LnArgs l;
-  l.in = x; l.ld_in = C0; l.M = M; l.cseg = C0;
-  l.gamma = swin_.patch_ln.g; l.beta = swin_.patch_ln.b; l.eps = 1e-5f;
-  l.out_f32 = x; l.ld32 = C0;
-  ln(l);
+  if (!fuse_ln) {
+    LnArgs l;
+    l.in = x; l.ld_in = C0; l.M = M; l.cseg = C0;
+    l.gamma = swin_.patch_ln.g; l.beta = swin_.patch_ln.b; l.eps = 1e-5f;
+    l.out_f32 = x; l.ld32 = C0;
+    ln(l);
+  }
   capture("swin.patch_embed", x, static_cast<size_t>(M) * C0, static_cast<size_t>(f0) * T0 * C0);
   for (int li = 0; li < split; ++li) {
     const SwinStageW& sw = swin_.stages[li];
@@ -1097,10 +1104,12 @@ void Engine::swin_body(const FrameSrc& frames, int F, const float* gumbel, float
   bf16* feat_ln = arena_.alloc<bf16>(static_cast<size_t>(F) * FL * kw_);
   float* feat512 = arena_.alloc<float>(static_cast<size_t>(F) * c.feat_dim);
   // Frames per pass: measured on B200 (profiles/r01_chunk_sweep.txt). With persistent kernels bigger passes win (fewer
-  // launches, fewer partial waves): 64/160 -> 196 utt/s, 96/192 -> 217, 320/640 -> 234, 320/1280 -> 239, 1280/1280 -> 236.
+  // launches, fewer partial waves): 64/160 -> 196 utt/s, 96/192 -> 217, 320/640 -> 234, 320/1280 -> 239, 1280/1280 -> 236;
+  // round-2 build with the fused half-block kernels and graph replay (profiles/r02_chunk_sweep.txt): 64/1280 -> 242, 160/1280 -> 250,
+  // 320/1280 -> 255, 640/1280 -> 258: L2-sized passes (64 frames = 77 MB of stage-1 residual) still lose to few large launches.
   // (fp32-grade mode keeps fp32 intermediates and split operands, 3-4x the bytes per frame: smaller passes)
   const int big = c.swin_chunk_late > 0 ? c.swin_chunk_late : (precise_ ? 320 : 1280);
-  const int small = c.swin_chunk > 0 ? c.swin_chunk : (precise_ ? 80 : 320);
+  const int small = c.swin_chunk > 0 ? c.swin_chunk : (precise_ ? 80 : 640);
   const SwinStageW& ss = swin_.stages[split];
   const size_t per_frame_split = static_cast<size_t>(ss.R) * ss.R * ss.C;
   for (int f0 = 0; f0 < F; f0 += big) {

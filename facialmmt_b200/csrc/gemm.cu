@@ -301,6 +301,9 @@ struct FastParams {
   int groups;      // active epilogue groups (2 or 4) == staging slabs == residual ring slots: compute-heavy GEMMs
                    // (large K) give the shared memory to the A/B pipeline instead of the epilogue rings
   int kbs;         // pair kernel: 64-column k-blocks per pipeline stage (1 or 2); stage_bytes covers all of them
+  const float* ln_gamma;   // LayerNorm epilogue (fp32 output, N <= block_n, N % 32 == 0): out = LN(acc + bias) * gamma + beta;
+  const float* ln_beta;    // one epilogue group owns a whole tile, so every thread sees all columns of its row
+  float ln_eps;
 };
 
 template <int ACT>
@@ -496,6 +499,69 @@ gemm_bf16_tcgen05_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __gr
       // Slab with running number c = res_base + s goes to group c % EPI_GROUPS (== its residual-ring slot): work
       // rotates over the groups from tile to tile, and every group consumes EVERY use of "its" ring slot in order,
       // which is what makes the parity waits on res_full/res_empty alias-free.
+      if (p.ln_gamma != nullptr) {
+        // ---- LayerNorm epilogue: the tile's rows are complete output rows (n_tiles == 1). Tiles rotate over the groups; the
+        // owner walks its row three times through TMEM (mean, centred variance, normalise) - TMEM reads are cheap, the
+        // row never touches shared or global memory before it is final.
+        if (static_cast<int>(res_base % static_cast<uint32_t>(p.groups)) == group) {
+          float sum = 0.f;
+          for (int s = 0; s < nsl; ++s) {
+            uint32_t v[32];
+            tmem_ld_32x32b_x32(t_row + static_cast<uint32_t>(s * 32), v);
+            tmem_ld_wait();
+            epi_math32<ACT_NONE>(v, p.bias, n0 + s * 32, p.N, 0);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) sum += __uint_as_float(v[j]);
+          }
+          const float mean = sum / static_cast<float>(ncols);
+          float var = 0.f;
+          for (int s = 0; s < nsl; ++s) {
+            uint32_t v[32];
+            tmem_ld_32x32b_x32(t_row + static_cast<uint32_t>(s * 32), v);
+            tmem_ld_wait();
+            epi_math32<ACT_NONE>(v, p.bias, n0 + s * 32, p.N, 0);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const float d = __uint_as_float(v[j]) - mean;
+              var = fmaf(d, d, var);
+            }
+          }
+          const float rstd = rsqrtf(var / static_cast<float>(ncols) + p.ln_eps);
+          for (int s = 0; s < nsl; ++s) {
+            const int gc0 = n0 + s * 32;
+            uint32_t v[32];
+            tmem_ld_32x32b_x32(t_row + static_cast<uint32_t>(s * 32), v);
+            tmem_ld_wait();
+            epi_math32<ACT_NONE>(v, p.bias, gc0, p.N, 0);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float4 g4 = __ldg(reinterpret_cast<const float4*>(p.ln_gamma + gc0) + j);
+              const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.ln_beta + gc0) + j);
+              v[4 * j] = __float_as_uint(fmaf((__uint_as_float(v[4 * j]) - mean) * rstd, g4.x, b4.x));
+              v[4 * j + 1] = __float_as_uint(fmaf((__uint_as_float(v[4 * j + 1]) - mean) * rstd, g4.y, b4.y));
+              v[4 * j + 2] = __float_as_uint(fmaf((__uint_as_float(v[4 * j + 2]) - mean) * rstd, g4.z, b4.z));
+              v[4 * j + 3] = __float_as_uint(fmaf((__uint_as_float(v[4 * j + 3]) - mean) * rstd, g4.w, b4.w));
+            }
+            if (elected) tma_store_wait_read<0>();
+            named_bar_sync(1 + group, 128);
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              *reinterpret_cast<uint4*>(my_out + ((j ^ sw) << 4)) = make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+            fence_proxy_async_smem();
+            named_bar_sync(1 + group, 128);
+            if (elected) {
+              tma_store_2d(&tmOut, out_slot, gc0, m0);
+              tma_store_commit();
+            }
+          }
+        }
+        res_base += 1u;   // LayerNorm mode: running TILE number of this CTA
+        tc_fence_before();
+        mbar_arrive(&tmem_empty_bar[acc]);
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1u;
+        continue;
+      }
       const uint32_t ng = static_cast<uint32_t>(p.groups);
       int s_first = nsl;   // inactive groups only take part in the accumulator hand-shake
       if (group < p.groups) s_first = static_cast<int>((static_cast<uint32_t>(group) + ng - res_base % ng) % ng);
@@ -1305,6 +1371,7 @@ cudaError_t launch_gemm(const GemmArgs& a, cudaStream_t stream) {
   if (attr_err != cudaSuccess) return attr_err;
 
   const bool one_out = (a.out_f32 != nullptr) != (a.out_bf16 != nullptr);
+  if (a.ln_gamma != nullptr && (a.force_generic || a.N > 256)) return cudaErrorInvalidValue;   // fast path only
   const bool fast = !a.force_generic && one_out && a.row_map == nullptr && a.rows_in == 0 && a.res_mod == 0 &&
                     (a.residual == nullptr || a.out_f32 != nullptr) && a.N >= 32;
   CUtensorMap tmA, tmB;
@@ -1313,7 +1380,7 @@ cudaError_t launch_gemm(const GemmArgs& a, cudaStream_t stream) {
     // -1 forbids (FMMT_NO_2CTA=1 in the environment forbids globally: A/B runs)
     static const bool no_pair = std::getenv("FMMT_NO_2CTA") != nullptr;
     static const bool pair_default = std::getenv("FMMT_2CTA") != nullptr;   // measured no faster than single CTAs
-    const bool want = a.two_cta > 0 || (a.two_cta == 0 && !no_pair && pair_default && a.K >= 256 && a.M >= 1024 && a.N >= 128);
+    const bool want = a.ln_gamma == nullptr && (a.two_cta > 0 || (a.two_cta == 0 && !no_pair && pair_default && a.K >= 256 && a.M >= 1024 && a.N >= 128));
     if (want) return launch_gemm_pair(a, stream);
   }
   if (fast) {
@@ -1337,6 +1404,7 @@ cudaError_t launch_gemm(const GemmArgs& a, cudaStream_t stream) {
     p.slab_cols = p.out_bf16 ? 64 : 32;
     p.has_res = a.residual != nullptr;
     p.block_n = a.block_n > 0 ? a.block_n : pick_block_n(a.M, a.N, a.K, g_num_sms, p.slab_cols, 256);
+    if (a.ln_gamma != nullptr) p.block_n = a.N;       // complete rows per tile
     if (p.block_n % p.slab_cols != 0 || p.block_n < 32 || p.block_n > 256) return cudaErrorInvalidValue;
     p.kbs = 1;
     p.stage_bytes = A_TILE_BYTES + p.block_n * BK * 2;
@@ -1373,6 +1441,10 @@ cudaError_t launch_gemm(const GemmArgs& a, cudaStream_t stream) {
     p.n_tiles = (a.N + p.block_n - 1) / p.block_n;
     p.num_kb = (a.K + BK - 1) / BK;
     p.bias = a.bias; p.act = a.act;
+    p.ln_gamma = a.ln_gamma; p.ln_beta = a.ln_beta; p.ln_eps = a.ln_eps;
+    if (a.ln_gamma != nullptr && (a.ln_beta == nullptr || p.n_tiles != 1 || p.out_bf16 || p.has_res || (a.N % 32) != 0 ||
+                                  a.act != ACT_NONE))
+      return cudaErrorInvalidValue;
     CUtensorMap tmRes, tmOut;
     if (use3d) {
       if (!make_tmap_kblocks(&tmA, a.A, a.M, a.K, a.lda, BM, 2)) return cudaErrorInvalidValue;

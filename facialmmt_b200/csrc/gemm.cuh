@@ -32,6 +32,9 @@ struct GemmArgs {
   const int* row_map = nullptr;     // dest = (r / map_period) * map_period + row_map[r % map_period]
   int map_period = 0;
   int rows_in = 0, rows_out = 0, row_off = 0;  // if rows_in>0: dest = (r/rows_in)*rows_out + row_off + r%rows_in
+  const float* ln_gamma = nullptr;  // LayerNorm over the N output columns fused into the epilogue (fp32 output, N <= 256,
+  const float* ln_beta = nullptr;   //   N % 32 == 0, no activation / residual): out = LN(A W^T + bias) * gamma + beta
+  float ln_eps = 1e-5f;
   int block_n = 0;                  // 0 = choose automatically
   int force_generic = 0;            // 1 = register-path epilogue even where the TMA-epilogue fast path applies
   int two_cta = 0;                  // CTA-pair kernel (cta_group::2, 256-row tiles): 0 = heuristic, 1 = force, -1 = never

@@ -1,6 +1,7 @@
 // HBM-bound kernels of the path: LayerNorm (+ window / patch-merge gathers), casts, patch im2col, Swin-cls tail,
 // frame filter + compaction, text embeddings, span extraction, cross-modal embedding, additive-attention pooling.
 // All are vectorised (16-byte accesses where the layout allows), warp-shuffle reductions, fp32 math.
+#include <cooperative_groups.h>
 #include "ops.cuh"
 #include "ptx.cuh"
 
@@ -504,6 +505,13 @@ __device__ __forceinline__ float2 ld2f(const __nv_bfloat16* p) {
 }
 __device__ __forceinline__ float2 ld2f(const float* p) { return *reinterpret_cast<const float2*>(p); }
 
+// AdditiveAttention pooling + classifier (src/models.py:171-188), one CLUSTER of POOL_SLICES CTAs per utterance: every CTA
+// computes the L scores and their softmax (cheap, L2-resident), pools ITS slice of the H columns (two halves of L per column,
+// four independent accumulators per thread), and hands the slice to CTA 0 of the cluster through distributed shared memory;
+// CTA 0 applies the classifier. Deterministic: no atomics, fixed summation order.
+constexpr int POOL_SLICES = 6;
+__device__ __forceinline__ float* cluster_map_rank0(float* p) { return cooperative_groups::this_cluster().map_shared_rank(p, 0); }
+__device__ __forceinline__ void pool_cluster_sync() { cooperative_groups::this_cluster().sync(); }
 template <typename TH>
 __global__ void __launch_bounds__(256) pool_classify_kernel(const float* __restrict__ x,
                                                             const TH* __restrict__ th,
@@ -511,11 +519,13 @@ __global__ void __launch_bounds__(256) pool_classify_kernel(const float* __restr
                                                             float bv, const float* __restrict__ wc,
                                                             const float* __restrict__ bc, int L, int H, int labels,
                                                             float* __restrict__ logits) {
-  extern __shared__ float sm[];  // scores[L] | y[H]
+  extern __shared__ float sm[];  // scores[L] | y[H] (complete only in CTA 0 of the cluster) | partial[256]
   float* s_sc = sm;
   float* s_y = sm + L;
+  float* s_part = s_y + H;
   __shared__ float s_red[8];
   const int u = blockIdx.x;
+  const unsigned int slice = blockIdx.y;   // == rank in the cluster (cluster dims 1 x POOL_SLICES x 1)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
   for (int t = warp; t < L; t += nwarps) {
     const TH* row = th + (static_cast<size_t>(u) * L + t) * H;
@@ -549,12 +559,33 @@ __global__ void __launch_bounds__(256) pool_classify_kernel(const float* __restr
   sum = 0.f;
   for (int w = 0; w < nwarps; ++w) sum += s_red[w];
   const float inv = 1.f / sum;
-  for (int c = threadIdx.x; c < H; c += blockDim.x) {
-    float acc = 0.f;
-    for (int t = 0; t < L; ++t) acc = fmaf(s_sc[t], x[(static_cast<size_t>(u) * L + t) * H + c], acc);
-    s_y[c] = acc * inv;
+  // pooled slice: columns [c0, c0 + cw); thread = (column, half of L)
+  const int cw = H / POOL_SLICES;          // 128 for H = 768
+  const int c0 = static_cast<int>(slice) * cw;
+  float* y0 = static_cast<float*>(cluster_map_rank0(s_y));
+  for (int cb = 0; cb < cw; cb += 128) {
+    const int c = cb + (threadIdx.x & 127);
+    const int half = threadIdx.x >> 7;
+    const int tb = half * ((L + 1) / 2), te = half == 0 ? (L + 1) / 2 : L;
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    if (c < cw) {
+      const float* xc = x + static_cast<size_t>(u) * L * H + c0 + c;
+      int t = tb;
+      for (; t + 4 <= te; t += 4) {
+        a0 = fmaf(s_sc[t], xc[static_cast<size_t>(t) * H], a0);
+        a1 = fmaf(s_sc[t + 1], xc[static_cast<size_t>(t + 1) * H], a1);
+        a2 = fmaf(s_sc[t + 2], xc[static_cast<size_t>(t + 2) * H], a2);
+        a3 = fmaf(s_sc[t + 3], xc[static_cast<size_t>(t + 3) * H], a3);
+      }
+      for (; t < te; ++t) a0 = fmaf(s_sc[t], xc[static_cast<size_t>(t) * H], a0);
+    }
+    s_part[threadIdx.x] = (a0 + a1) + (a2 + a3);
+    __syncthreads();
+    if (half == 0 && c < cw) y0[c0 + c] = (s_part[threadIdx.x] + s_part[threadIdx.x + 128]) * inv;   // into CTA 0's smem
+    __syncthreads();
   }
-  __syncthreads();
+  pool_cluster_sync();
+  if (slice != 0) return;
   for (int k = warp; k < labels; k += nwarps) {
     float acc = 0.f;
     for (int c = lane; c < H; c += 32) acc = fmaf(s_y[c], wc[k * H + c], acc);
@@ -716,11 +747,19 @@ cudaError_t launch_pool_classify(const float* x, const __nv_bfloat16* th, const 
                                  const float* wv, float bv, const float* wc, const float* bc, int U, int L, int H,
                                  int labels, float* logits, cudaStream_t stream) {
   if (U <= 0 || L <= 0 || (H % 64) != 0 || ((th == nullptr) == (th_f32 == nullptr))) return cudaErrorInvalidValue;
-  const size_t smem = (L + H) * sizeof(float);
-  if (smem > 48 * 1024) return cudaErrorInvalidValue;
-  if (th != nullptr) pool_classify_kernel<__nv_bfloat16><<<U, 256, smem, stream>>>(x, th, mask, wv, bv, wc, bc, L, H, labels, logits);
-  else pool_classify_kernel<float><<<U, 256, smem, stream>>>(x, th_f32, mask, wv, bv, wc, bc, L, H, labels, logits);
-  return cudaGetLastError();
+  const size_t smem = (L + H + 256) * sizeof(float);
+  if (smem > 48 * 1024 || (H % (POOL_SLICES * 2)) != 0) return cudaErrorInvalidValue;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(U, POOL_SLICES, 1);
+  cfg.blockDim = dim3(256, 1, 1);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 1; attr[0].val.clusterDim.y = POOL_SLICES; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  if (th != nullptr) return cudaLaunchKernelEx(&cfg, pool_classify_kernel<__nv_bfloat16>, x, th, mask, wv, bv, wc, bc, L, H, labels, logits);
+  return cudaLaunchKernelEx(&cfg, pool_classify_kernel<float>, x, th_f32, mask, wv, bv, wc, bc, L, H, labels, logits);
 }
 
 cudaError_t launch_gather_rows(const float* in, const int* map, int period, int C, int M, float* out,

@@ -55,7 +55,14 @@ struct LnQkvParams {
   const int* gather;
   const float* gamma; const float* beta; float eps;
   const float* bias;
+  long long* trace;   // optional [8 tiles][32] clock64 stamps of CTA 0 (debug)
+  int dbg;            // debug probes: 1 = skip the x_raw stores, 2 = skip the output stores (wrong results)
 };
+
+#define TRACE(slot)                                                                          \
+  do {                                                                                       \
+    if (p.trace != nullptr && blockIdx.x == 0 && i < 8) p.trace[i * 32 + (slot)] = clock64(); \
+  } while (0)
 
 template <int C>
 __global__ void __launch_bounds__(THREADS, 1)
@@ -122,7 +129,9 @@ ln_qkv_stream_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_const
       uint32_t u = 0;
       uint32_t cnt[2] = {0u, 0u};    // uses of each TMEM buffer so far (chunk j of a tile goes to buffer j & 1)
       for (int i = 0; i < n_local; ++i) {
+        TRACE(7);
         mbar_wait(&a_full, i & 1u, 91);
+        TRACE(8);
         tc_fence_after();
         for (int j = 0; j < p.chunks; ++j) {
           const int bn = p.N - j * BN < BN ? p.N - j * BN : BN;
@@ -144,6 +153,7 @@ ln_qkv_stream_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_const
             umma_commit(&w_empty[sl]);
           }
           umma_commit(&d_full[b]);
+          TRACE(9 + j);
         }
         umma_commit(&a_empty);       // every MMA of this tile has been issued: A may be rewritten once they complete
       }
@@ -155,31 +165,51 @@ ln_qkv_stream_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_const
     const int team = t >> 4;                     // rows team + 16 * pass
     constexpr int Q = K::NKB;                    // float4 per lane per row (one per 64-column k-block)
     constexpr int BATCH = 12 / Q;                // rows in flight per thread
+    // row -> source row of x (the composed roll + window_partition gather works within a frame of T tokens)
+    auto src_row = [&](int row) -> int {
+      if (p.gather == nullptr) return row;
+      const int fr = row / p.T;
+      return fr * p.T + __ldg(p.gather + (row - fr * p.T));
+    };
     for (int i = 0; i < n_local; ++i) {
       const int tile = static_cast<int>(blockIdx.x) + i * static_cast<int>(gridDim.x);
-      const long long m0 = static_cast<long long>(tile) * TILE_M;
+      const int m0 = tile * TILE_M;
       bool waited = false;
+      if (t == 0) TRACE(0);
 #pragma unroll 1
       for (int pass0 = 0; pass0 < 8; pass0 += BATCH) {
         float4 xv[BATCH][Q];
+        // every load of the batch is issued before the first store: x and x_raw may alias as far as the compiler knows,
+        // and a store placed between two rows' loads serialises their HBM round trips
+        int src[BATCH];
 #pragma unroll
         for (int bq = 0; bq < BATCH; ++bq) {
-          const long long row = m0 + team + 16 * (pass0 + bq);
-          if (row < p.M) {
-            long long src = row;
-            if (p.gather != nullptr) {
-              const long long fr = row / p.T;
-              src = fr * p.T + __ldg(p.gather + static_cast<int>(row - fr * p.T));
+          const int row = m0 + team + 16 * (pass0 + bq);
+          src[bq] = row < p.M ? src_row(row) : -1;
+        }
+#pragma unroll
+        for (int bq = 0; bq < BATCH; ++bq) {
+#pragma unroll
+          for (int q = 0; q < Q; ++q)
+            xv[bq][q] = src[bq] >= 0 ? __ldcg(reinterpret_cast<const float4*>(p.x + static_cast<size_t>(src[bq]) * C + 4 * l16 + 64 * q))
+                                     : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        if (pass0 + BATCH >= 8 && i + 1 < n_local) {
+          // pull the next tile's rows towards L2 while this tile is multiplied (the LayerNorm is on the critical path: the A
+          // tile is single-buffered)
+          const int nrow = m0 + static_cast<int>(gridDim.x) * TILE_M + (t >> 1);
+          if (nrow < p.M) prefetch_l2_bulk(p.x + static_cast<size_t>(src_row(nrow)) * C + (t & 1) * (C / 2), C * 2);
+        }
+        if (t == 0 && pass0 == BATCH) TRACE(27);
+        if (p.x_raw != nullptr && !(p.dbg & 1)) {
+#pragma unroll
+          for (int bq = 0; bq < BATCH; ++bq) {
+            const int row = m0 + team + 16 * (pass0 + bq);
+            if (src[bq] >= 0) {
+#pragma unroll
+              for (int q = 0; q < Q; ++q)
+                *reinterpret_cast<float4*>(p.x_raw + static_cast<size_t>(row) * C + 4 * l16 + 64 * q) = xv[bq][q];
             }
-#pragma unroll
-            for (int q = 0; q < Q; ++q) xv[bq][q] = __ldcg(reinterpret_cast<const float4*>(p.x + src * C + 4 * l16 + 64 * q));
-            if (p.x_raw != nullptr) {
-#pragma unroll
-              for (int q = 0; q < Q; ++q) *reinterpret_cast<float4*>(p.x_raw + row * C + 4 * l16 + 64 * q) = xv[bq][q];
-            }
-          } else {
-#pragma unroll
-            for (int q = 0; q < Q; ++q) xv[bq][q] = make_float4(0.f, 0.f, 0.f, 0.f);
           }
         }
         float rstd[BATCH];
@@ -206,9 +236,12 @@ ln_qkv_stream_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_const
           v += __shfl_xor_sync(0xffffffffu, v, 8);
           rstd[bq] = rsqrtf(v * (1.0f / C) + p.eps);
         }
+        if (t == 0) TRACE(1 + pass0 / BATCH);
+        if (t == 0 && pass0 == BATCH) TRACE(28);
         if (!waited) {
           mbar_wait_relaxed(&a_empty, (i & 1u) ^ 1u, 94, 500);   // every MMA of the previous tile has consumed the A tile
           waited = true;
+          if (t == 0) TRACE(5);
         }
 #pragma unroll
         for (int q = 0; q < Q; ++q) {
@@ -227,9 +260,11 @@ ln_qkv_stream_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_const
             *reinterpret_cast<uint2*>(dst) = make_uint2(pack_bf16(o0, o1), pack_bf16(o2, o3));
           }
         }
+        if (t == 0 && pass0 == BATCH) TRACE(29);
       }
       fence_proxy_async_smem();
       mbar_arrive(&a_full);
+      if (t == 0) TRACE(6);
     }
   } else {
     // ------------------------------------------------------------------ drain groups: accumulator -> + bias -> bf16 -> TMA store
@@ -248,6 +283,7 @@ ln_qkv_stream_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_const
         const int bn = p.N - j * BN < BN ? p.N - j * BN : BN;
         const uint32_t b = j & 1u;
         mbar_wait(&d_full[b], cnt[b] & 1u, 95);
+        if (threadIdx.x == 0) TRACE(16 + j);
         ++cnt[b];
         tc_fence_after();
         const int nslab = bn >> 6;
@@ -279,13 +315,14 @@ ln_qkv_stream_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_const
             *reinterpret_cast<uint4*>(my_out + ((q ^ sw) << 4)) = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
           fence_proxy_async_smem();
           named_bar_sync(1 + group, 128);
-          if (elected) {
+          if (elected && !(p.dbg & 2)) {
             tma_store_2d(&tmOut, slab, j * BN + 64 * sl, m0);   // rows >= M are clipped by the tensor map
             tma_store_commit();
           }
         }
         tc_fence_before();
         mbar_arrive(&d_empty[b]);     // this thread's reads of the chunk's accumulator are done
+        if (threadIdx.x == 0) TRACE(22 + j);
       }
     }
     if (elected) tma_store_wait_all();
@@ -318,7 +355,7 @@ cudaError_t launch_c(const LnQkvArgs& a, cudaStream_t stream) {
   if (!make_tmap_2d(&tmWrem, a.w, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, a.N, C, a.ldw, 64, rem > 0 ? rem : BN)) return cudaErrorInvalidValue;
   if (!make_tmap_2d(&tmOut, a.out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, a.M, a.N, a.ldo, 64, TILE_M)) return cudaErrorInvalidValue;
   LnQkvParams p{a.x, a.x_raw, a.M, a.T, (a.M + TILE_M - 1) / TILE_M, (a.N + BN - 1) / BN, a.N, a.gather, a.gamma, a.beta, a.eps,
-                a.bias};
+                a.bias, a.trace, a.dbg};
   const int grid = p.num_tiles < num_sms ? p.num_tiles : num_sms;
   ln_qkv_stream_kernel<C><<<grid, THREADS, K::SMEM + 1024, stream>>>(tmW, tmWrem, tmOut, p);
   return cudaGetLastError();

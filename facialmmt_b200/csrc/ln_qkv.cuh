@@ -22,6 +22,8 @@ struct LnQkvArgs {
   int N = 0;                       // output columns (3C), a multiple of 64
   __nv_bfloat16* out = nullptr;    // bf16 [M, ldo]
   int ldo = 0;
+  long long* trace = nullptr;      // debug: [8][32] clock64 stamps of CTA 0
+  int dbg = 0;                     // debug probes (see ln_qkv.cu); results are wrong when set
 };
 inline bool ln_qkv_supported(int C, int N) { return (C == 192 || C == 384) && N > 0 && (N % 64) == 0; }
 cudaError_t launch_ln_qkv(const LnQkvArgs& a, cudaStream_t stream);

@@ -102,6 +102,10 @@ __device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* tm) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(tm)) : "memory");
 }
+// Pull `bytes` (a multiple of 16, 16-byte aligned) of global memory towards L2 without a destination.
+__device__ __forceinline__ void prefetch_l2_bulk(const void* gptr, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gptr), "r"(bytes) : "memory");
+}
 // 2-D tiled load global -> shared, completion signalled on an mbarrier (complete_tx::bytes).
 __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* tm, uint64_t* bar, int c0, int c1) {
   asm volatile(

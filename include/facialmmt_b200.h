@@ -203,6 +203,12 @@ FMMT_API int fmmt_op_gemm(const void* A_bf16, int lda, const void* W_bf16, int l
                           const float* bias, int act, const float* residual, int ldr, float* out_f32, int ldo32,
                           void* out_bf16, int ldo16, const int* row_map, int map_period, int block_n, void* stream);
 
+/* Linear + LayerNorm over the N output columns in ONE kernel (the LayerNorm runs in the GEMM epilogue, where a thread owns a
+ * whole accumulator row): out = LayerNorm(A W^T + bias) * gamma + beta, fp32 [M, ldo]. N <= 256, N % 32 == 0. Used for
+ * PatchEmbed: Conv2d(3,96,k4,s4) as a K = 48 GEMM followed by norm_layer(96) (Swin_Transformer.py:402-412). */
+FMMT_API int fmmt_op_gemm_ln(const void* A_bf16, int lda, const void* W_bf16, int ldw, int M, int N, int K, const float* bias,
+                             const float* gamma, const float* beta, float eps, float* out_f32, int ldo, void* stream);
+
 /* LayerNorm over rows gathered from `nseg` segments (see csrc/ops.cuh LnArgs); biased variance, eps inside sqrt. */
 FMMT_API int fmmt_op_layernorm(const float* in, int ld_in, int M, int nseg, int cseg, const int* map, int map_period,
                                int src_period, const float* gamma, const float* beta, float eps, float* out_f32,
@@ -245,6 +251,14 @@ FMMT_API int fmmt_op_swin_attn(const float* x, float* x_out, int M, int T, const
 FMMT_API int fmmt_op_swin_mlp_stream(float* x, int M, int C, const float* gamma, const float* beta, float eps,
                                      const void* w1_bf16, int ldw1, const float* b1, const void* w2_bf16, int ldw2,
                                      const float* b2, int copies, void* stream);
+
+/* norm1 + roll + window_partition + WindowAttention's qkv Linear of a Swin block with C = 192 / 384 as ONE tcgen05 kernel
+ * (Swin_Transformer.py:238-247 and :119):  out[r] = LayerNorm(x[g(r)]) @ W^T + bias (bf16 [M, ldo]),  x_raw[r] = x[g(r)] (fp32, the
+ * block's residual stream in window order; may be NULL when gather is NULL). gather: device int32 [T] or NULL (identity),
+ * M % T == 0 when given. w_bf16 = qkv.weight as bf16 [N, ldw] (nn.Linear layout), N % 64 == 0. flags: 0. */
+FMMT_API int fmmt_op_ln_qkv(const float* x, float* x_raw, int M, int C, int T, const int* gather, const float* gamma,
+                            const float* beta, float eps, const void* w_bf16, int ldw, const float* bias, int N,
+                            void* out_bf16, int ldo, int flags, void* stream);
 
 /* Multi-head attention core, head_dim 64: softmax(scale * q k^T + (1 - key_mask) * mask_neg) v.
  * q rows (b*Lq+i), k/v rows (b*Lk+j), head h at columns [64h, 64h+64). key_mask fp32 (B,Lk) of 0/1 or NULL. */

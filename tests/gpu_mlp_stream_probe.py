@@ -8,7 +8,8 @@ from facialmmt_b200._lib import check, cur_stream, ptr
 
 lib = _lib.load()
 g = torch.Generator().manual_seed(1)
-for C, Mbig in ((192, 50176), (384, 31360)):
+MB = int(os.environ.get("MBIG", "0"))
+for C, Mbig in ((192, MB or 50176), (384, MB or 31360)):
     H = 4 * C
     gam, bet = (1 + 0.2 * torch.randn(C, generator=g)).cuda(), (0.2 * torch.randn(C, generator=g)).cuda()
     w1 = (torch.randn(H, C, generator=g) / math.sqrt(C)).cuda().to(torch.bfloat16).contiguous()

@@ -182,3 +182,34 @@ def test_gemm_inplace_residual_stress(lib):
             ref = x + A.float() @ W.float().t() + b
             err = (y - ref).abs().max().item()
             assert err < 2e-2, f"M={M} rep={rep}: max err {err}"
+
+
+@pytest.mark.parametrize("M,N,K", [(3136, 96, 48), (128 * 148 * 5 + 77, 96, 48), (1000, 256, 192), (260, 32, 64)])
+def test_gemm_layernorm_epilogue(lib, M, N, K):
+    """Linear + LayerNorm in one kernel (fmmt_op_gemm_ln; PatchEmbed = Conv2d(3,96,k4,s4) as a K = 48 GEMM + norm_layer(96),
+    Swin_Transformer.py:402-412): same bf16 operands, fp32 accumulate, fp32 two-pass LayerNorm on both sides."""
+    from facialmmt_b200._lib import check, cur_stream, ptr
+    g = torch.Generator(device="cpu").manual_seed(M + 3 * N + K)
+    A = torch.randn(M, K, generator=g).to(torch.bfloat16)
+    W = (torch.randn(N, K, generator=g) / K ** 0.5).to(torch.bfloat16)
+    b = torch.randn(N, generator=g)
+    gam = 1.0 + 0.2 * torch.randn(N, generator=g)
+    bet = 0.1 * torch.randn(N, generator=g)
+    ref = torch.nn.functional.layer_norm(A.float() @ W.float().t() + b, (N,), gam, bet, 1e-5)
+    Ad, Wd, bd, gd, btd = (t.cuda() for t in (A, W, b, gam, bet))
+    out = torch.full((M, N), float("nan"), device="cuda")
+    first = None
+    for rep in range(2):
+        out.fill_(float("nan"))
+        check(lib.fmmt_op_gemm_ln(ptr(Ad), K, ptr(Wd), K, M, N, K, ptr(bd), ptr(gd), ptr(btd), 1e-5, ptr(out), N, cur_stream()),
+              "fmmt_op_gemm_ln")
+        torch.cuda.synchronize()
+        if rep == 0:
+            first = out.clone()
+    assert lib.fmmt_debug_timeout(1) == 0
+    got = out.cpu()
+    assert torch.isfinite(got).all()
+    err = (got - ref).abs().max().item()
+    print(f"\ngemm+LN {M}x{N}x{K}: err {err:.3e}")
+    assert err < 2e-3                      # unit-variance rows: the accumulation-order noise of the GEMM, rescaled by 1/std
+    assert torch.equal(first, out)
