@@ -505,13 +505,29 @@ __device__ __forceinline__ float2 ld2f(const __nv_bfloat16* p) {
 }
 __device__ __forceinline__ float2 ld2f(const float* p) { return *reinterpret_cast<const float2*>(p); }
 
-// AdditiveAttention pooling + classifier (src/models.py:171-188), one CLUSTER of POOL_SLICES CTAs per utterance: every CTA
-// computes the L scores and their softmax (cheap, L2-resident), pools ITS slice of the H columns (two halves of L per column,
-// four independent accumulators per thread), and hands the slice to CTA 0 of the cluster through distributed shared memory;
-// CTA 0 applies the classifier. Deterministic: no atomics, fixed summation order.
+// AdditiveAttention pooling + classifier (src/models.py:171-188), one CLUSTER of POOL_SLICES CTAs per utterance:
+//   1. the L score rows are split over the CTAs (four rows in flight per warp); every score is written into the score array
+//      of EVERY CTA of the cluster through distributed shared memory;
+//   2. every CTA runs the softmax over the L scores (cheap) and pools ITS slice of H / POOL_SLICES columns: thread = (float4
+//      column, one of eight row groups), four rows in flight, fixed-order reduction over the row groups in shared memory;
+//   3. the slices are written into CTA 0's y vector (distributed shared memory), CTA 0 applies the classifier.
+// Deterministic: no atomics, fixed summation order.
 constexpr int POOL_SLICES = 6;
-__device__ __forceinline__ float* cluster_map_rank0(float* p) { return cooperative_groups::this_cluster().map_shared_rank(p, 0); }
+template <typename T>
+__device__ __forceinline__ T* cluster_map(T* p, unsigned int rank) { return cooperative_groups::this_cluster().map_shared_rank(p, rank); }
 __device__ __forceinline__ void pool_cluster_sync() { cooperative_groups::this_cluster().sync(); }
+
+template <typename TH>
+__device__ __forceinline__ float score_row(const TH* __restrict__ row, const float* __restrict__ wv, int H, int lane) {
+  float acc = 0.f;
+  for (int c = lane * 2; c < H; c += 64) {
+    const float2 v = ld2f(row + c);
+    acc = fmaf(v.x, wv[c], acc);
+    acc = fmaf(v.y, wv[c + 1], acc);
+  }
+  return acc;
+}
+
 template <typename TH>
 __global__ void __launch_bounds__(256) pool_classify_kernel(const float* __restrict__ x,
                                                             const TH* __restrict__ th,
@@ -519,26 +535,40 @@ __global__ void __launch_bounds__(256) pool_classify_kernel(const float* __restr
                                                             float bv, const float* __restrict__ wc,
                                                             const float* __restrict__ bc, int L, int H, int labels,
                                                             float* __restrict__ logits) {
-  extern __shared__ float sm[];  // scores[L] | y[H] (complete only in CTA 0 of the cluster) | partial[256]
-  float* s_sc = sm;
-  float* s_y = sm + L;
-  float* s_part = s_y + H;
+  extern __shared__ __align__(16) float sm[];  // partial[8][128] | y[H] (complete only in CTA 0 of the cluster) | scores[L]
+  float* s_part = sm;
+  float* s_y = sm + 8 * 128;
+  float* s_sc = s_y + H;
   __shared__ float s_red[8];
   const int u = blockIdx.x;
   const unsigned int slice = blockIdx.y;   // == rank in the cluster (cluster dims 1 x POOL_SLICES x 1)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
-  for (int t = warp; t < L; t += nwarps) {
-    const TH* row = th + (static_cast<size_t>(u) * L + t) * H;
-    float acc = 0.f;
-    for (int c = lane * 2; c < H; c += 64) {
-      const float2 v = ld2f(row + c);
-      acc = fmaf(v.x, wv[c], acc);
-      acc = fmaf(v.y, wv[c + 1], acc);
+  pool_cluster_sync();   // every CTA of the cluster is running before its shared memory is written remotely
+  // ---- 1. scores of a contiguous block of rows per CTA (four per warp at a time), broadcast to the cluster
+  {
+    const int per = (L + POOL_SLICES - 1) / POOL_SLICES;      // rows of this CTA: t = slice * per + i
+    const int tb = static_cast<int>(slice) * per, te = min(L, tb + per);
+    for (int t0 = tb + warp * 4; t0 < te; t0 += nwarps * 4) {
+      float acc[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int t = min(t0 + q, te - 1);
+        acc[q] = score_row(th + (static_cast<size_t>(u) * L + t) * H, wv, H, lane);
+      }
+#pragma unroll
+      for (int q = 0; q < 4; ++q) acc[q] = warp_sum(acc[q]);
+      if (lane < POOL_SLICES) {
+        float* dst = cluster_map(s_sc, static_cast<unsigned int>(lane));
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int t = t0 + q;
+          if (t < te) dst[t] = mask[static_cast<size_t>(u) * L + t] == 0.f ? -INFINITY : acc[q] + bv;
+        }
+      }
     }
-    acc = warp_sum(acc);
-    if (lane == 0) s_sc[t] = mask[static_cast<size_t>(u) * L + t] == 0.f ? -INFINITY : acc + bv;
   }
-  __syncthreads();
+  pool_cluster_sync();
+  // ---- 2. softmax over the L scores
   float mx = -INFINITY;
   for (int t = threadIdx.x; t < L; t += blockDim.x) mx = fmaxf(mx, s_sc[t]);
   mx = warp_max(mx);
@@ -559,30 +589,39 @@ __global__ void __launch_bounds__(256) pool_classify_kernel(const float* __restr
   sum = 0.f;
   for (int w = 0; w < nwarps; ++w) sum += s_red[w];
   const float inv = 1.f / sum;
-  // pooled slice: columns [c0, c0 + cw); thread = (column, half of L)
-  const int cw = H / POOL_SLICES;          // 128 for H = 768
+  // ---- 3. pooled slice: columns [c0, c0 + cw), cw = H / POOL_SLICES (a multiple of 4, <= 128)
+  const int cw = H / POOL_SLICES;
   const int c0 = static_cast<int>(slice) * cw;
-  float* y0 = static_cast<float*>(cluster_map_rank0(s_y));
-  for (int cb = 0; cb < cw; cb += 128) {
-    const int c = cb + (threadIdx.x & 127);
-    const int half = threadIdx.x >> 7;
-    const int tb = half * ((L + 1) / 2), te = half == 0 ? (L + 1) / 2 : L;
-    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-    if (c < cw) {
-      const float* xc = x + static_cast<size_t>(u) * L * H + c0 + c;
-      int t = tb;
-      for (; t + 4 <= te; t += 4) {
-        a0 = fmaf(s_sc[t], xc[static_cast<size_t>(t) * H], a0);
-        a1 = fmaf(s_sc[t + 1], xc[static_cast<size_t>(t + 1) * H], a1);
-        a2 = fmaf(s_sc[t + 2], xc[static_cast<size_t>(t + 2) * H], a2);
-        a3 = fmaf(s_sc[t + 3], xc[static_cast<size_t>(t + 3) * H], a3);
+  {
+    const int c4 = threadIdx.x & 31;       // float4 column of the slice
+    const int lg = threadIdx.x >> 5;       // row group: t = lg, lg + 8, ...
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (4 * c4 < cw) {
+      const float* xc = x + static_cast<size_t>(u) * L * H + c0 + 4 * c4;
+      for (int t0 = lg; t0 < L; t0 += 32) {
+        float4 v[4];
+        float w[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int t = t0 + 8 * q;
+          w[q] = t < L ? s_sc[t] : 0.f;
+          v[q] = t < L ? *reinterpret_cast<const float4*>(xc + static_cast<size_t>(t) * H) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          a.x = fmaf(w[q], v[q].x, a.x); a.y = fmaf(w[q], v[q].y, a.y);
+          a.z = fmaf(w[q], v[q].z, a.z); a.w = fmaf(w[q], v[q].w, a.w);
+        }
       }
-      for (; t < te; ++t) a0 = fmaf(s_sc[t], xc[static_cast<size_t>(t) * H], a0);
+      *reinterpret_cast<float4*>(s_part + lg * 128 + 4 * c4) = a;
     }
-    s_part[threadIdx.x] = (a0 + a1) + (a2 + a3);
     __syncthreads();
-    if (half == 0 && c < cw) y0[c0 + c] = (s_part[threadIdx.x] + s_part[threadIdx.x + 128]) * inv;   // into CTA 0's smem
-    __syncthreads();
+    if (static_cast<int>(threadIdx.x) < cw) {
+      float acc = 0.f;
+#pragma unroll
+      for (int g = 0; g < 8; ++g) acc += s_part[g * 128 + threadIdx.x];
+      cluster_map(s_y, 0u)[c0 + threadIdx.x] = acc * inv;           // into CTA 0's y
+    }
   }
   pool_cluster_sync();
   if (slice != 0) return;
@@ -747,8 +786,8 @@ cudaError_t launch_pool_classify(const float* x, const __nv_bfloat16* th, const 
                                  const float* wv, float bv, const float* wc, const float* bc, int U, int L, int H,
                                  int labels, float* logits, cudaStream_t stream) {
   if (U <= 0 || L <= 0 || (H % 64) != 0 || ((th == nullptr) == (th_f32 == nullptr))) return cudaErrorInvalidValue;
-  const size_t smem = (L + H + 256) * sizeof(float);
-  if (smem > 48 * 1024 || (H % (POOL_SLICES * 2)) != 0) return cudaErrorInvalidValue;
+  const size_t smem = (L + H + 8 * 128) * sizeof(float);
+  if (smem > 48 * 1024 || (H % (POOL_SLICES * 4)) != 0 || H / POOL_SLICES > 128) return cudaErrorInvalidValue;
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(U, POOL_SLICES, 1);
   cfg.blockDim = dim3(256, 1, 1);
