@@ -13,7 +13,7 @@
 //     instruction cover it;
 //   * two drain groups read the accumulator 64 columns at a time, add the bias, pack bf16 into a 128B-swizzled slab and hand
 //     it to a TMA store.
-// Shared memory (C = 384): A 96 KB | weight ring 3 x 32 KB | output slabs 2 x 16 KB.
+// Shared memory: A 96 KB (C = 384: one tile; C = 192: two tiles of 48 KB) | weight ring 3 x 32 KB | output slabs 2 x 16 KB.
 #include "ln_qkv.cuh"
 
 #include <mutex>
@@ -40,10 +40,12 @@ struct Cfg {
   static_assert(C == 192 || C == 384, "LN + qkv: C = 192 or 384");
   static constexpr int NKB = C / 64;
   static constexpr int PIECE = BN * 128;        // one k-block of a chunk's weights: 256 rows x 64 bf16 = 32 KB
-  static constexpr int NSLOT = C == 384 ? 3 : 4;    // k-blocks in flight (shared memory: A 96 / 48 KB + slots + 32 KB)
-  static constexpr int A_BYTES = NKB * 16384;
+  static constexpr int NSLOT = 3;                   // k-blocks in flight
+  static constexpr int A_BYTES = NKB * 16384;       // one normalised 128-row tile
+  static constexpr int NA = C == 384 ? 1 : 2;       // A tiles: at C = 192 two fit, so the LayerNorm of tile i + 1 overlaps the
+                                                    // MMAs of tile i; at C = 384 (96 KB per tile) they alternate
   static constexpr int OFF_A = 0;
-  static constexpr int OFF_W = A_BYTES;
+  static constexpr int OFF_W = NA * A_BYTES;
   static constexpr int OFF_OUT = OFF_W + NSLOT * PIECE;
   static constexpr int SMEM = OFF_OUT + 2 * 16384;
   static_assert(SMEM + 1024 <= 227 * 1024, "shared memory budget");
@@ -70,7 +72,7 @@ ln_qkv_stream_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_const
                      const __grid_constant__ CUtensorMap tmOut, const LnQkvParams p) {
   using K = Cfg<C>;
   extern __shared__ uint8_t smem_raw[];
-  __shared__ uint64_t a_full, a_empty, w_full[MAX_SLOTS], w_empty[MAX_SLOTS], d_full[2], d_empty[2];
+  __shared__ uint64_t a_full[2], a_empty[2], w_full[MAX_SLOTS], w_empty[MAX_SLOTS], d_full[2], d_empty[2];
   __shared__ uint32_t tmem_base_slot;
 
   const int warp = threadIdx.x >> 5;
@@ -79,8 +81,10 @@ ln_qkv_stream_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_const
   uint8_t* smem = smem_raw + (smem_base - smem_u32(smem_raw));
 
   if (threadIdx.x == 0) {
-    mbar_init(&a_full, LN_WARPS * 32);
-    mbar_init(&a_empty, 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&a_full[s], LN_WARPS * 32);
+      mbar_init(&a_empty[s], 1);
+    }
     for (int s = 0; s < MAX_SLOTS; ++s) {
       mbar_init(&w_full[s], 1);
       mbar_init(&w_empty[s], 1);
@@ -130,7 +134,9 @@ ln_qkv_stream_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_const
       uint32_t cnt[2] = {0u, 0u};    // uses of each TMEM buffer so far (chunk j of a tile goes to buffer j & 1)
       for (int i = 0; i < n_local; ++i) {
         TRACE(7);
-        mbar_wait(&a_full, i & 1u, 91);
+        const uint32_t ab = K::NA == 2 ? (i & 1u) : 0u;                       // A tile buffer of this tile and the parity
+        const uint32_t apar = K::NA == 2 ? ((i >> 1) & 1u) : (i & 1u);        // of its current use
+        mbar_wait(&a_full[ab], apar, 91);
         TRACE(8);
         tc_fence_after();
         for (int j = 0; j < p.chunks; ++j) {
@@ -146,7 +152,7 @@ ln_qkv_stream_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_const
             const uint32_t sl = u % K::NSLOT;
             mbar_wait(&w_full[sl], (u / K::NSLOT) & 1u, 93);
             tc_fence_after();
-            const uint64_t a = make_smem_desc_sw128(smem_base + K::OFF_A + kb * 16384);
+            const uint64_t a = make_smem_desc_sw128(smem_base + K::OFF_A + ab * K::A_BYTES + kb * 16384);
             const uint64_t w = make_smem_desc_sw128(smem_base + K::OFF_W + sl * K::PIECE);
 #pragma unroll
             for (int k = 0; k < 4; ++k) umma_bf16(d, a + 2 * k, w + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
@@ -155,7 +161,7 @@ ln_qkv_stream_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_const
           umma_commit(&d_full[b]);
           TRACE(9 + j);
         }
-        umma_commit(&a_empty);       // every MMA of this tile has been issued: A may be rewritten once they complete
+        umma_commit(&a_empty[ab]);   // every MMA of this tile has been issued: its A tile may be rewritten once they complete
       }
     }
   } else if (warp >= LN_WARP0) {
@@ -175,6 +181,8 @@ ln_qkv_stream_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_const
       const int tile = static_cast<int>(blockIdx.x) + i * static_cast<int>(gridDim.x);
       const int m0 = tile * TILE_M;
       bool waited = false;
+      const uint32_t ab = K::NA == 2 ? (i & 1u) : 0u;
+      const uint32_t apar = K::NA == 2 ? ((i >> 1) & 1u) : (i & 1u);
       if (t == 0) TRACE(0);
 #pragma unroll 1
       for (int pass0 = 0; pass0 < 8; pass0 += BATCH) {
@@ -239,7 +247,7 @@ ln_qkv_stream_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_const
         if (t == 0) TRACE(1 + pass0 / BATCH);
         if (t == 0 && pass0 == BATCH) TRACE(28);
         if (!waited) {
-          mbar_wait_relaxed(&a_empty, (i & 1u) ^ 1u, 94, 500);   // every MMA of the previous tile has consumed the A tile
+          mbar_wait_relaxed(&a_empty[ab], apar ^ 1u, 94, 500);   // the MMAs of the previous use of this A tile are complete
           waited = true;
           if (t == 0) TRACE(5);
         }
@@ -256,14 +264,14 @@ ln_qkv_stream_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_const
             const float o1 = fmaf(xv[bq][q].y * rstd[bq], g4.y, be4.y);
             const float o2 = fmaf(xv[bq][q].z * rstd[bq], g4.z, be4.z);
             const float o3 = fmaf(xv[bq][q].w * rstd[bq], g4.w, be4.w);
-            uint8_t* dst = smem + K::OFF_A + q * 16384 + r * 128 + ((((kc >> 3) ^ (r & 7))) << 4) + (kc & 7) * 2;
+            uint8_t* dst = smem + K::OFF_A + ab * K::A_BYTES + q * 16384 + r * 128 + ((((kc >> 3) ^ (r & 7))) << 4) + (kc & 7) * 2;
             *reinterpret_cast<uint2*>(dst) = make_uint2(pack_bf16(o0, o1), pack_bf16(o2, o3));
           }
         }
         if (t == 0 && pass0 == BATCH) TRACE(29);
       }
       fence_proxy_async_smem();
-      mbar_arrive(&a_full);
+      mbar_arrive(&a_full[ab]);
       if (t == 0) TRACE(6);
     }
   } else {
