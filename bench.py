@@ -40,21 +40,39 @@ WORKLOADS = {
 }
 
 
-def ncu_traffic(kernel_prefix="gemm_bf16_tcgen05_tma_kernel"):
-    """DRAM bytes per launch of the dominant kernel class from the committed `ncu --set full` capture of THIS build's
-    launch geometry (profiles/r02_ncu_top_kernels.json; falls back to the round-1 capture)."""
-    for name in ("r02_ncu_top_kernels.json", "r01_ncu_full_swin160_top_kernels.json"):
-        p = os.path.join(ROOT, "profiles", name)
-        try:
-            rows = [r for r in json.load(open(p)) if r["kernel"].startswith(kernel_prefix)]
-            if not rows:
-                continue
-            b = sum((r["dram_rd_MB"] + r["dram_wr_MB"]) * 1e6 for r in rows) / len(rows)
-            return b, (f"mean dram__bytes_read+write over {len(rows)} captured launches of {kernel_prefix} (ncu --set full, "
-                       f"cold L2: ncu flushes caches between kernels), profiles/{name}")
-        except Exception:
-            continue
-    return None, None
+GEMM_CLASS_KERNELS = ("gemm_bf16_tcgen05", "swin_mlp", "swin_attn96", "ln_qkv_stream")   # ncu names of the tcgen05 GEMM-class kernels
+# event-profile label prefix -> ncu kernel name, for the single dominant kernel's DRAM traffic
+LABEL_TO_NCU = {"mlp_fused C=384": "swin_mlp_stream_kernel<384>", "mlp_fused C=192": "swin_mlp_stream_kernel<192>",
+                "mlp_fused C=96": "swin_mlp96_fused_kernel", "attn_fused C=96": "swin_attn96_fused_kernel",
+                "ln_qkv C=384": "ln_qkv_stream_kernel<384>", "ln_qkv C=192": "ln_qkv_stream_kernel<192>"}
+
+
+def ncu_traffic():
+    """Mean DRAM bytes per GEMM-class launch (dram__bytes_read.sum + dram__bytes_write.sum) from the committed ncu metric pass
+    over one whole step of THIS workload and launch geometry (profiles/r02_launches_final.json, made by tools/gpu_ncu_final.sh
+    + tools/ncu_summary.py)."""
+    p = os.path.join(ROOT, "profiles", "r02_launches_final.json")
+    try:
+        ks = [k for k in json.load(open(p))["kernels"] if k["kernel"].startswith(GEMM_CLASS_KERNELS)]
+        n = sum(k["launches"] for k in ks)
+        b = sum(k["dram_MB_per_launch"] * 1e6 * k["launches"] for k in ks) / n
+        return b, (f"mean dram__bytes_read.sum + dram__bytes_write.sum over the {n} GEMM-class launches of one U=8 step (ncu metric "
+                   f"pass, cold L2: ncu flushes caches between kernels), profiles/r02_launches_final.json")
+    except Exception:
+        return None, None
+
+
+def ncu_kernel_traffic(label):
+    """DRAM bytes of ONE launch of the kernel behind an event-profile label, from the `ncu --set full` capture of the same launch
+    geometry (profiles/r02_ncu_top_kernels.json)."""
+    want = next((v for k, v in LABEL_TO_NCU.items() if label.startswith(k)), None)
+    try:
+        rows = [r for r in json.load(open(os.path.join(ROOT, "profiles", "r02_ncu_top_kernels.json"))) if r["kernel"] == want]
+        if not rows:
+            return None
+        return sum((r["dram_rd_MB"] + r["dram_wr_MB"]) * 1e6 for r in rows) / len(rows)
+    except Exception:
+        return None
 
 
 def peaks():
@@ -438,18 +456,28 @@ def run_ours(args):
             m.set_profile(False)
         pk = peaks()
         # every tcgen05 GEMM-class launch: Linear-layer GEMMs, fused MLP kernels, fused attention half-blocks
-        gem = [v for k, v in prof.items() if k.startswith(("gemm ", "mlp_fused", "attn_fused"))]
+        gem_items = [(k, v) for k, v in prof.items() if k.startswith(("gemm ", "mlp_fused", "attn_fused", "ln_qkv"))]
+        gem = [v for _, v in gem_items]
         g_ms = sum(v["ms"] for v in gem); g_fl = sum(v["flops"] for v in gem); g_n = sum(v["launches"] for v in gem)
         all_ms = sum(v["ms"] for v in prof.values())
         achieved = g_fl / (g_ms * 1e-3) / 1e12 if g_ms > 0 else 0.0
         traffic, traffic_src = ncu_traffic()
-        roof = {"bound": "tensor", "kernel": "tcgen05 GEMM-class launches of the step (gemm_bf16_tcgen05_tma_kernel, fused MLP "
-                                             "and fused attention half-block kernels: every Linear layer of the path)",
+        roof = {"bound": "tensor", "kernel": "tcgen05 GEMM-class launches of the step (gemm_bf16_tcgen05_tma_kernel, fused MLP, fused "
+                                             "attention half-block and LN+qkv kernels: every Linear layer of the path)",
                 "achieved": achieved, "peak": pk["tf_sustained"], "unit": "TFLOP/s",
                 "frac": achieved / pk["tf_sustained"], "traffic": traffic, "traffic_source": traffic_src,
                 "peak_source": pk["source"] + ", sustained bf16 figure (kernels timed inside a long step)",
                 "launches_per_step": g_n, "flops_per_launch": g_fl / max(g_n, 1), "avg_launch_ms": g_ms / max(g_n, 1),
                 "share_of_step_kernel_time": g_ms / all_ms if all_ms > 0 else None}
+        # the single dominant kernel (largest share of the step), same accounting
+        dk, dv = max(gem_items, key=lambda kv: kv[1]["ms"])
+        d_tf = dv["flops"] / (dv["ms"] * 1e-3) / 1e12
+        roof["dominant_kernel"] = {"kernel": dk, "ncu_name": next((v for k, v in LABEL_TO_NCU.items() if dk.startswith(k)), None),
+                                   "launches_per_step": dv["launches"], "avg_launch_ms": dv["ms"] / dv["launches"],
+                                   "flops_per_launch": dv["flops"] / dv["launches"], "achieved": d_tf,
+                                   "frac": d_tf / pk["tf_sustained"], "share_of_step_kernel_time": dv["ms"] / all_ms,
+                                   "algorithmic_bytes_per_launch": dv["bytes"] / dv["launches"],
+                                   "traffic": ncu_kernel_traffic(dk)}
         top = sorted(prof.items(), key=lambda kv: -kv[1]["ms"])[:6]
         roof["top_kernels"] = [{"kernel": k, "ms": round(v["ms"], 4), "launches": v["launches"],
                                 "tflops": round(v["flops"] / max(v["ms"], 1e-9) / 1e9, 1),
