@@ -12,7 +12,7 @@ for f in gpurun_out/r02_bench_n1_final.json gpurun_out/r02_bench_n1_u8ingest.jso
   python - "$f" <<'PY'
 import json, sys
 try:
-    d = json.load(open(sys.argv[1]))
+    d = json.loads([l for l in open(sys.argv[1]) if l.startswith("{")][-1])
     print(sys.argv[1].split('/')[-1], round(d["value"], 2), d["unit"], "ms/step", round(d["ms_per_step"], 2), "e2e", d.get("e2e", {}).get("value"),
           "parity", d.get("parity_checked"), "frac", d.get("roofline", {}) and round(d["roofline"]["frac"], 3))
 except Exception as e:
