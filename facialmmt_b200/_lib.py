@@ -89,6 +89,8 @@ SIGNATURES = {
                                   c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
     "fmmt_op_swin_mlp_stream": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_float, c_void_p, c_int, c_void_p,
                                         c_void_p, c_int, c_void_p, c_int, c_void_p]),
+    "fmmt_op_swin_mlp_pair": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_float, c_void_p, c_int, c_void_p,
+                                      c_void_p, c_int, c_void_p, c_void_p]),
     "fmmt_op_ln_qkv": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_int,
                                c_void_p, c_int, c_void_p, c_int, c_int, c_void_p]),
     "fmmt_op_span_extract": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p,

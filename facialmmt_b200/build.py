@@ -17,7 +17,7 @@ CSRC = PKG_DIR / "csrc"
 BUILD_DIR = CSRC / "build"
 LIB_PATH = PKG_DIR / "libfacialmmt_b200.so"
 
-SOURCES = ["gemm.cu", "mlp_fused.cu", "mlp_stream.cu", "kernels.cu", "attention.cu", "attn_fused.cu", "ln_qkv.cu", "ingest.cu",
+SOURCES = ["gemm.cu", "mlp_fused.cu", "mlp_stream.cu", "mlp_pair.cu", "kernels.cu", "attention.cu", "attn_fused.cu", "ln_qkv.cu", "ingest.cu",
            "umma_probe.cu", "engine.cu", "capi.cu"]
 
 NVCC_FLAGS = [

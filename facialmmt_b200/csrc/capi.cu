@@ -159,8 +159,8 @@ FMMT_API int64_t fmmt_profile_read(fmmt_handle* h, char* buf, int64_t buf_len) {
 }
 
 FMMT_API uint32_t fmmt_debug_timeout(int reset) {
-  unsigned int* addrs[6] = {watchdog_addr_gemm(), watchdog_addr_mlp96(), watchdog_addr_mlp_stream(), watchdog_addr_attn(),
-                            watchdog_addr_attn96(), watchdog_addr_ln_qkv()};
+  unsigned int* addrs[7] = {watchdog_addr_gemm(), watchdog_addr_mlp96(), watchdog_addr_mlp_stream(), watchdog_addr_attn(),
+                            watchdog_addr_attn96(), watchdog_addr_ln_qkv(), watchdog_addr_mlp_pair()};
   cudaDeviceSynchronize();
   uint32_t first = 0;
   for (unsigned int* a : addrs) {
@@ -312,6 +312,19 @@ FMMT_API int fmmt_op_swin_mlp_stream(float* x, int M, int C, const float* gamma,
   if (copies < 0) { a.trace = static_cast<long long*>(stream); count_launch(); return check_cuda(launch_mlp_stream(a, nullptr), "fmmt_op_swin_mlp_stream"); }
   count_launch();
   return check_cuda(launch_mlp_stream(a, S(stream)), "fmmt_op_swin_mlp_stream");
+}
+
+FMMT_API int fmmt_op_swin_mlp_pair(float* x, int M, int C, const float* gamma, const float* beta, float eps,
+                                   const void* w1_bf16, int ldw1, const float* b1, const void* w2_bf16, int ldw2,
+                                   const float* b2, void* stream) {
+  if (!x || !gamma || !beta || !w1_bf16 || !w2_bf16 || !b1 || !b2)
+    return set_error(FMMT_ERR_INVALID, "fmmt_op_swin_mlp_pair: null pointer");
+  MlpStreamArgs a;
+  a.x = x; a.M = M; a.C = C; a.gamma = gamma; a.beta = beta; a.eps = eps;
+  a.w1 = static_cast<const __nv_bfloat16*>(w1_bf16); a.ldw1 = ldw1; a.b1 = b1;
+  a.w2 = static_cast<const __nv_bfloat16*>(w2_bf16); a.ldw2 = ldw2; a.b2 = b2;
+  count_launch();
+  return check_cuda(launch_mlp_pair(a, S(stream)), "fmmt_op_swin_mlp_pair");
 }
 
 FMMT_API int fmmt_op_ln_qkv(const float* x, float* x_raw, int M, int C, int T, const int* gather, const float* gamma,

@@ -743,7 +743,10 @@ void Engine::mlp_stream(float* x, int M, int C, const SwinBlockW& bw) {
   a.gamma = bw.ln2.g; a.beta = bw.ln2.b; a.eps = 1e-5f;
   a.w1 = bw.fc1.w; a.ldw1 = bw.fc1.ld; a.b1 = bw.fc1.b;
   a.w2 = bw.fc2.w; a.ldw2 = bw.fc2.ld; a.b2 = bw.fc2.b;
-  ck(launch_mlp_stream(a, st_), "mlp_stream");
+  // CTA-pair variant (mlp_pair.cu): bit-identical, measured 2 % (C = 384) / 6 % (C = 192) SLOWER than the single-CTA kernel
+  // (tests/gpu_mlp_stream_probe.py), so it is opt-in
+  static const bool use_pair = std::getenv("FMMT_MLP_PAIR") != nullptr;
+  ck(use_pair ? launch_mlp_pair(a, st_) : launch_mlp_stream(a, st_), "mlp_stream");
   if (prof_) prof_end(e1);
 }
 
@@ -867,10 +870,10 @@ int Engine::run(Fn&& body, cudaStream_t st, const std::vector<unsigned long long
   body();
   {
     // pipeline watchdog hand-off: collect + clear the per-translation-unit words, copy to the pinned status word
-    unsigned int* addrs[6] = {watchdog_addr_gemm(), watchdog_addr_mlp96(), watchdog_addr_mlp_stream(), watchdog_addr_attn(),
-                              watchdog_addr_attn96(), watchdog_addr_ln_qkv()};
+    unsigned int* addrs[7] = {watchdog_addr_gemm(), watchdog_addr_mlp96(), watchdog_addr_mlp_stream(), watchdog_addr_attn(),
+                              watchdog_addr_attn96(), watchdog_addr_ln_qkv(), watchdog_addr_mlp_pair()};
     count_launch();
-    ck(launch_collect_status(addrs, 6, status_dev_, st_), "collect_status");
+    ck(launch_collect_status(addrs, 7, status_dev_, st_), "collect_status");
     ck(cudaMemcpyAsync(status_host_, status_dev_, sizeof(unsigned int), cudaMemcpyDeviceToHost, st_), "status copy");
   }
   if (capture) {

@@ -14,6 +14,7 @@
 #include "gemm.cuh"
 #include "ln_qkv.cuh"
 #include "mlp_fused.cuh"
+#include "mlp_pair.cuh"
 #include "mlp_stream.cuh"
 #include "ops.cuh"
 

@@ -252,6 +252,12 @@ FMMT_API int fmmt_op_swin_mlp_stream(float* x, int M, int C, const float* gamma,
                                      const void* w1_bf16, int ldw1, const float* b1, const void* w2_bf16, int ldw2,
                                      const float* b2, int copies, void* stream);
 
+/* The same half-block on CTA PAIRS (tcgen05 cta_group::2, clusters of two CTAs on 256 rows: every CTA holds its 128 rows of
+ * the activations and half of every weight chunk, so the weight bytes streamed per SM halve). Same arguments and results. */
+FMMT_API int fmmt_op_swin_mlp_pair(float* x, int M, int C, const float* gamma, const float* beta, float eps,
+                                   const void* w1_bf16, int ldw1, const float* b1, const void* w2_bf16, int ldw2,
+                                   const float* b2, void* stream);
+
 /* norm1 + roll + window_partition + WindowAttention's qkv Linear of a Swin block with C = 192 / 384 as ONE tcgen05 kernel
  * (Swin_Transformer.py:238-247 and :119):  out[r] = LayerNorm(x[g(r)]) @ W^T + bias (bf16 [M, ldo]),  x_raw[r] = x[g(r)] (fp32, the
  * block's residual stream in window order; may be NULL when gather is NULL). gather: device int32 [T] or NULL (identity),

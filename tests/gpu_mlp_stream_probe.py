@@ -48,7 +48,11 @@ for C, Mbig in ((192, MB or 50176), (384, MB or 31360)):
     xs = [(torch.randn(M, C, generator=g)).cuda() for _ in range(4)]
     h16 = torch.empty(M, C, device="cuda", dtype=torch.bfloat16)
     hid16 = torch.empty(M, H, device="cuda", dtype=torch.bfloat16)
-    for name, fn in (("un-fused", lambda x: unfused(x, h16, hid16)), ("fused", fused)):
+    def fused_pair(x):
+        check(lib.fmmt_op_swin_mlp_pair(ptr(x), x.shape[0], C, ptr(gam), ptr(bet), 1e-5, ptr(w1), C, ptr(b1), ptr(w2), H, ptr(b2),
+                                        cur_stream()))
+
+    for name, fn in (("un-fused", lambda x: unfused(x, h16, hid16)), ("fused", fused), ("fused CTA-pair", fused_pair)):
         for x in xs:
             fn(x)
         torch.cuda.synchronize()

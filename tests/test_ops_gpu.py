@@ -167,9 +167,10 @@ def test_swin_mlp_fused_repeatable(lib):
     assert torch.equal(y1, y2)
 
 
-def _mlp_stream_case(lib, M, C, seed):
-    """fused LN + fc1 + GELU + fc2 + residual with streamed weights (fmmt_op_swin_mlp_stream) against an fp32 torch
-    restatement that rounds the same operands to bf16 (LN output, weights, hidden)."""
+def _mlp_stream_case(lib, M, C, seed, pair=False):
+    """fused LN + fc1 + GELU + fc2 + residual with streamed weights (fmmt_op_swin_mlp_stream, or its CTA-pair variant
+    fmmt_op_swin_mlp_pair) against an fp32 torch restatement that rounds the same operands to bf16 (LN output, weights,
+    hidden)."""
     from facialmmt_b200._lib import check, cur_stream, ptr
     g = _gen(seed)
     H = 4 * C
@@ -183,8 +184,12 @@ def _mlp_stream_case(lib, M, C, seed):
     hid = bf(torch.nn.functional.gelu(h @ w1.float().t() + b1))
     ref = x + (hid @ w2.float().t() + b2)
     y = x.clone()
-    check(lib.fmmt_op_swin_mlp_stream(ptr(y), M, C, ptr(gam), ptr(bet), 1e-5, ptr(w1), C, ptr(b1), ptr(w2), H, ptr(b2),
-                                      1, cur_stream()))
+    if pair:
+        check(lib.fmmt_op_swin_mlp_pair(ptr(y), M, C, ptr(gam), ptr(bet), 1e-5, ptr(w1), C, ptr(b1), ptr(w2), H, ptr(b2),
+                                        cur_stream()))
+    else:
+        check(lib.fmmt_op_swin_mlp_stream(ptr(y), M, C, ptr(gam), ptr(bet), 1e-5, ptr(w1), C, ptr(b1), ptr(w2), H, ptr(b2),
+                                          1, cur_stream()))
     torch.cuda.synchronize()
     assert lib.fmmt_debug_timeout(1) == 0, "pipeline wait timed out inside the streamed fused MLP kernel"
     return y, ref
@@ -202,4 +207,23 @@ def test_swin_mlp_stream(lib, M, C):
 def test_swin_mlp_stream_repeatable(lib):
     y1, _ = _mlp_stream_case(lib, 148 * 128 * 2 + 5, 384, seed=11)
     y2, _ = _mlp_stream_case(lib, 148 * 128 * 2 + 5, 384, seed=11)
+    assert torch.equal(y1, y2)
+
+
+@pytest.mark.parametrize("C", [192, 384])
+@pytest.mark.parametrize("M", [256, 100, 1, 129, 257, 74 * 256, 74 * 256 * 2 + 77, 31360])
+def test_swin_mlp_pair(lib, M, C):
+    """CTA-pair (cta_group::2) variant: same contract, and bit-identical to the single-CTA kernel (same operand values, same
+    accumulation order per output element)."""
+    y, ref = _mlp_stream_case(lib, M, C, seed=M + C, pair=True)
+    err = (y - ref).abs().max().item()
+    assert torch.isfinite(y).all()
+    assert err < 2e-2 * max(1.0, ref.abs().max().item() / 8), f"M={M} C={C}: max abs err {err}"
+    y1, _ = _mlp_stream_case(lib, M, C, seed=M + C, pair=False)
+    assert torch.equal(y, y1)
+
+
+def test_swin_mlp_pair_repeatable(lib):
+    y1, _ = _mlp_stream_case(lib, 74 * 256 * 2 + 5, 384, seed=11, pair=True)
+    y2, _ = _mlp_stream_case(lib, 74 * 256 * 2 + 5, 384, seed=11, pair=True)
     assert torch.equal(y1, y2)
