@@ -385,7 +385,7 @@ def run_ours(args):
     # ---- parity of THIS configuration (outside the timed regions, rank 0, N=1): frames-per-pass invariance bit for bit
     parity = None
     ref_runner = None
-    if rank == 0 and world == 1 and not args.no_parity:
+    if rank == 0 and not args.no_parity:      # rank-local (no collective): also at N > 1
         parity = {}
         frames0 = dev["faces"][0]                                        # first utterance's 160 frames
         g0 = dev["gumbel"][:frames0.shape[0]]
