@@ -30,6 +30,7 @@ struct PackError : std::runtime_error {
 Engine::Engine(const fmmt_config& cfg) : cfg_(cfg) {
   precise_ = cfg.precision == FMMT_PRECISION_FP32;
   kw_ = precise_ ? 3 : 1;
+  branches_ = std::getenv("FMMT_NO_BRANCHES") == nullptr;
 }
 
 Engine::~Engine() {
@@ -38,6 +39,11 @@ Engine::~Engine() {
   for (cudaEvent_t e : ev_pool_) cudaEventDestroy(e);
   drop_graphs();
   if (graph_stream_) cudaStreamDestroy(graph_stream_);
+  for (int k = 0; k < 2; ++k) {
+    if (side_[k]) cudaStreamDestroy(side_[k]);
+    if (ev_join_[k]) cudaEventDestroy(ev_join_[k]);
+  }
+  if (ev_fork_) cudaEventDestroy(ev_fork_);
   for (void* p : dev_ptrs_) cudaFree(p);
   if (ws_) cudaFree(ws_);
   if (status_host_) cudaFreeHost(status_host_);
@@ -802,6 +808,7 @@ int Engine::run(Fn&& body, cudaStream_t st, const std::vector<unsigned long long
   st_ = st;
   first_err_ = cudaSuccess;
   err_.clear();
+  pending_[0] = pending_[1] = false;
   const bool graphable = graph_on_ && !prof_ && caps_.empty() && !key.empty();
   GraphEntry* ge = nullptr;
   if (graphable) {
@@ -1169,6 +1176,40 @@ int Engine::swin_forward_u8(const uint8_t* crops, int F, int crop_h, int crop_w,
 }
 
 // =================================================================================================== fusion forward
+// Branch the stream-ordered launch sequence: everything issued on the forward's stream so far happens-before the branch;
+// returns the main stream (to hand back to join_from). No-ops in the sizing pass and after an error.
+cudaStream_t Engine::fork_to(int k) {
+  cudaStream_t main_stream = st_;
+  // (fp32-grade mode releases and re-uses scratch inside a branch, lin_to_operand: it stays on one stream)
+  if (!branches_ || precise_ || arena_.dry() || first_err_ != cudaSuccess) return main_stream;
+  if (side_[k] == nullptr) {
+    ck(cudaStreamCreateWithFlags(&side_[k], cudaStreamNonBlocking), "side stream");
+    ck(cudaEventCreateWithFlags(&ev_join_[k], cudaEventDisableTiming), "join event");
+  }
+  if (ev_fork_ == nullptr) ck(cudaEventCreateWithFlags(&ev_fork_, cudaEventDisableTiming), "fork event");
+  if (first_err_ != cudaSuccess) return main_stream;
+  ck(cudaEventRecord(ev_fork_, main_stream), "fork record");
+  ck(cudaStreamWaitEvent(side_[k], ev_fork_, 0), "fork wait");
+  st_ = side_[k];
+  return main_stream;
+}
+
+// End of branch k: remember its completion on its event and redirect the following launches back to the main stream
+// (which does NOT wait yet).
+void Engine::branch_done(int k, cudaStream_t main_stream) {
+  if (st_ == main_stream) return;               // the fork was a no-op
+  ck(cudaEventRecord(ev_join_[k], side_[k]), "branch record");
+  st_ = main_stream;
+  pending_[k] = true;
+}
+
+// The main stream waits for branch k (if one was started).
+void Engine::join_wait(int k) {
+  if (!pending_[k]) return;
+  pending_[k] = false;
+  ck(cudaStreamWaitEvent(st_, ev_join_[k], 0), "join wait");
+}
+
 void Engine::enc_layers(const std::vector<EncLayerW>& layers, float* x32, bf16* x16, int U, int L, int H, int heads,
                         int ffn, const float* mask01, float mask_neg, float eps) {
   const int M = U * L;
@@ -1215,7 +1256,7 @@ void Engine::meld_encoder(const MeldEncW& m, const float* in, int in_dim, int U,
 }
 
 void Engine::cmt_encoder(const CmtW& cw, const float* xq, int Lq, int q_total, int q_off, const float* xkv, int Lk,
-                         int kv_total, int kv_off, int U, float* out32, bf16* out16, int out_total, int out_off) {
+                         int kv_total, int kv_off, int U, float* out32, bf16* out16, int out_total, int out_off, bool keep_scratch) {
   const int H = cfg_.hidden;
   const int Mq = U * Lq, Mk = U * Lk;
   const size_t mark = arena_.mark();
@@ -1261,7 +1302,7 @@ void Engine::cmt_encoder(const CmtW& cw, const float* xq, int Lq, int q_total, i
   nf.out_f32 = out32; nf.ld32 = H; nf.out_bf16 = out16; nf.ld16 = H * kw_; nf.split = precise_;
   nf.rows_in = Lq; nf.rows_out = out_total; nf.row_off = out_off;
   ln(nf);
-  arena_.release(mark);
+  if (!keep_scratch) arena_.release(mark);   // a concurrent branch's scratch stays reserved until the caller has joined it
 }
 
 void Engine::pool_head(const float* x32, const bf16* x16, const float* mask01, int U, int L, float* logits) {
@@ -1287,11 +1328,37 @@ void Engine::multimodal_body(const int64_t* ids, const int64_t* mask, const int6
   const int Ut = text_row != nullptr ? n_text : U;
   const int H = c.hidden, D = c.text_hidden, M = Ut * L;
   const int Lt = c.text_len, La = c.audio_len, Lv = c.vision_len;
-  // ---- text (src/models.py:99-107)
+  // The audio encoder, the vision encoder and the text encoder are independent until the fusion (src/models.py:99-166): the
+  // first two run on side streams beside the text encoder (their ~55 small launches hide under its 168), and so do the two
+  // directions of each CrossmodalTransformer pair. Buffers of concurrent branches never alias: every branch's scratch stays
+  // reserved in the arena until after its join.
   int* pos = arena_.alloc<int>(M);
   float* tx32 = arena_.alloc<float>(static_cast<size_t>(M) * D);
   bf16* tx16 = arena_.alloc<bf16>(static_cast<size_t>(M) * D * kw_);
   float* tmask = arena_.alloc<float>(M);
+  float* ax32 = arena_.alloc<float>(static_cast<size_t>(U) * La * H);
+  bf16* ax16 = arena_.alloc<bf16>(static_cast<size_t>(U) * La * H * kw_);
+  float* vx32 = arena_.alloc<float>(static_cast<size_t>(U) * Lv * H);
+  bf16* vx16 = arena_.alloc<bf16>(static_cast<size_t>(U) * Lv * H * kw_);
+  float* t768 = arena_.alloc<float>(static_cast<size_t>(M) * H);
+  float* txt = arena_.alloc<float>(static_cast<size_t>(U) * Lt * H);
+  float* txt_mask = arena_.alloc<float>(static_cast<size_t>(U) * Lt);
+  const int Lta = Lt + La, Ltot = Lta + Lv;
+  float* ta = arena_.alloc<float>(static_cast<size_t>(U) * Lta * H);
+  float* fused = arena_.alloc<float>(static_cast<size_t>(U) * Ltot * H);
+  bf16* fused16 = arena_.alloc<bf16>(static_cast<size_t>(U) * Ltot * H * kw_);
+  float* fmask = arena_.alloc<float>(static_cast<size_t>(U) * Ltot);
+  const size_t mk_enc = arena_.mark();
+  // ---- audio / vision self-attention encoders (src/models.py:154-166) on the side streams
+  {
+    cudaStream_t main_stream = fork_to(0);
+    meld_encoder(audio_, audio, c.audio_dim, U, La, audio_mask, ax32, ax16);
+    branch_done(0, main_stream);                // the main stream waits for it in join_wait(0) below
+    main_stream = fork_to(1);
+    meld_encoder(vision_, vision, c.vision_dim + c.num_labels, U, Lv, vision_mask, vx32, vx16);
+    branch_done(1, main_stream);
+  }
+  // ---- text (src/models.py:99-107) on the main stream
   if (!arena_.dry() && first_err_ == cudaSuccess) {
     count_launch(2);
     ck(launch_text_embed(ids, pos, Ut, L, c.text_kind == FMMT_TEXT_ROBERTA, c.pad_id, text_.word, text_.pos, text_.type0,
@@ -1299,46 +1366,38 @@ void Engine::multimodal_body(const int64_t* ids, const int64_t* mask, const int6
        "text_embed");
   }
   OP(launch_cast_i64_f32(mask, tmask, M, st_), "mask cast");
-  {
-    const size_t mk = arena_.mark();
-    enc_layers(text_.layers, tx32, tx16, Ut, L, D, c.text_heads, c.text_ffn, tmask, -3.4028234663852886e38f, c.text_eps);
-    arena_.release(mk);
-  }
-  float* t768 = arena_.alloc<float>(static_cast<size_t>(M) * H);
+  enc_layers(text_.layers, tx32, tx16, Ut, L, D, c.text_heads, c.text_ffn, tmask, -3.4028234663852886e38f, c.text_eps);
   GemmArgs gt;
   gt.out_f32 = t768; gt.ldo32 = H;
   gemm_lin(tx16, D, M, text_.out, gt);
   capture("mm.text768", t768, static_cast<size_t>(M) * H);
-  float* txt = arena_.alloc<float>(static_cast<size_t>(U) * Lt * H);
-  float* txt_mask = arena_.alloc<float>(static_cast<size_t>(U) * Lt);
   OP(launch_span_extract(t768, sep, idx, text_row, U, L, H, Lt, c.text_kind == FMMT_TEXT_ROBERTA ? 2 : 1, txt, txt_mask, st_),
      "span_extract");
   capture("mm.text", txt, static_cast<size_t>(U) * Lt * H);
-  // ---- audio / vision self-attention encoders (src/models.py:154-166)
-  float* ax32 = arena_.alloc<float>(static_cast<size_t>(U) * La * H);
-  bf16* ax16 = arena_.alloc<bf16>(static_cast<size_t>(U) * La * H * kw_);
-  float* vx32 = arena_.alloc<float>(static_cast<size_t>(U) * Lv * H);
-  bf16* vx16 = arena_.alloc<bf16>(static_cast<size_t>(U) * Lv * H * kw_);
-  {
-    const size_t mk = arena_.mark();
-    meld_encoder(audio_, audio, c.audio_dim, U, La, audio_mask, ax32, ax16);
-    arena_.release(mk);
-    meld_encoder(vision_, vision, c.vision_dim + c.num_labels, U, Lv, vision_mask, vx32, vx16);
-    arena_.release(mk);
-  }
+  join_wait(0);
+  join_wait(1);
+  arena_.release(mk_enc);                        // encoder scratch of all three branches: later launches are ordered after them
   capture("mm.audio", ax32, static_cast<size_t>(U) * La * H);
   capture("mm.vision", vx32, static_cast<size_t>(U) * Lv * H);
-  // ---- cross-modal fusion (src/models.py:169-179); concat along time by writing slices of one buffer
-  const int Lta = Lt + La, Ltot = Lta + Lv;
-  float* ta = arena_.alloc<float>(static_cast<size_t>(U) * Lta * H);
-  float* fused = arena_.alloc<float>(static_cast<size_t>(U) * Ltot * H);
-  bf16* fused16 = arena_.alloc<bf16>(static_cast<size_t>(U) * Ltot * H * kw_);
-  float* fmask = arena_.alloc<float>(static_cast<size_t>(U) * Ltot);
-  cmt_encoder(cmt_ta_, txt, Lt, Lt, 0, ax32, La, La, 0, U, ta, nullptr, Lta, 0);
-  cmt_encoder(cmt_ta_, ax32, La, La, 0, txt, Lt, Lt, 0, U, ta, nullptr, Lta, Lt);
+  // ---- cross-modal fusion (src/models.py:169-179); concat along time by writing slices of one buffer; the two directions
+  // of a pair are independent (they share weights and write disjoint slices)
+  {
+    cudaStream_t main_stream = fork_to(0);
+    cmt_encoder(cmt_ta_, txt, Lt, Lt, 0, ax32, La, La, 0, U, ta, nullptr, Lta, 0, true);
+    branch_done(0, main_stream);
+    cmt_encoder(cmt_ta_, ax32, La, La, 0, txt, Lt, Lt, 0, U, ta, nullptr, Lta, Lt, true);
+    join_wait(0);
+    arena_.release(mk_enc);
+  }
   capture("mm.ta", ta, static_cast<size_t>(U) * Lta * H);
-  cmt_encoder(cmt_tav_, ta, Lta, Lta, 0, vx32, Lv, Lv, 0, U, fused, fused16, Ltot, 0);
-  cmt_encoder(cmt_tav_, vx32, Lv, Lv, 0, ta, Lta, Lta, 0, U, fused, fused16, Ltot, Lta);
+  {
+    cudaStream_t main_stream = fork_to(0);
+    cmt_encoder(cmt_tav_, ta, Lta, Lta, 0, vx32, Lv, Lv, 0, U, fused, fused16, Ltot, 0, true);
+    branch_done(0, main_stream);
+    cmt_encoder(cmt_tav_, vx32, Lv, Lv, 0, ta, Lta, Lta, 0, U, fused, fused16, Ltot, Lta, true);
+    join_wait(0);
+    arena_.release(mk_enc);
+  }
   capture("mm.fused", fused, static_cast<size_t>(U) * Ltot * H);
   OP(launch_concat_masks(txt_mask, Lt, audio_mask, La, vision_mask, Lv, fmask, U, st_), "concat_masks");
   pool_head(fused, fused16, fmask, U, Ltot, logits);

@@ -223,7 +223,7 @@ class Engine {
   void meld_encoder(const MeldEncW& m, const float* in, int in_dim, int U, int L, const float* mask01, float* x32,
                     bf16* x16);
   void cmt_encoder(const CmtW& c, const float* xq, int Lq, int q_total, int q_off, const float* xkv, int Lk, int kv_total,
-                   int kv_off, int U, float* out32, bf16* out16, int out_total, int out_off);
+                   int kv_off, int U, float* out32, bf16* out16, int out_total, int out_off, bool keep_scratch = false);
   void pool_head(const float* x32, const bf16* x16, const float* mask01, int U, int L, float* logits);
   void multimodal_body(const int64_t* ids, const int64_t* mask, const int64_t* sep, const float* audio,
                        const float* audio_mask, const float* vision, const float* vision_mask, const int64_t* idx, int U,
@@ -240,6 +240,18 @@ class Engine {
   std::unordered_map<unsigned long long, GraphEntry> graphs_;
   bool graph_on_ = false;
   cudaStream_t graph_stream_ = nullptr;   // private capture stream
+  // Side streams for the independent branches of the fusion forward (audio / vision encoders beside the text encoder, the two
+  // directions of a CrossmodalTransformer pair): fork_to(k) makes side stream k wait for everything issued on the forward's
+  // stream so far and redirects the following launches to it; branch_done(k, main) switches back, join_wait(k) makes the main
+  // stream wait for the branch. Inside a graph capture the same calls produce parallel branches of the graph. Scratch memory of
+  // concurrent branches must not be released until after the join (cmt_encoder's keep_scratch).
+  cudaStream_t side_[2] = {nullptr, nullptr};
+  cudaEvent_t ev_fork_ = nullptr, ev_join_[2] = {nullptr, nullptr};
+  bool branches_ = true;                  // FMMT_NO_BRANCHES=1 runs the fusion forward on one stream
+  bool pending_[2] = {false, false};
+  cudaStream_t fork_to(int k);
+  void branch_done(int k, cudaStream_t main_stream);
+  void join_wait(int k);
   void drop_graphs();
 
   fmmt_config cfg_;

@@ -46,3 +46,38 @@ def test_graph_replay_is_bit_identical_and_reads_live_buffers():
     ref2 = step()
     assert torch.equal(got, ref2)
     assert not torch.equal(ref2, ref1)
+
+
+def test_parallel_branches_match_the_single_stream_forward(monkeypatch):
+    """The fusion forward runs the audio / vision encoders beside the text encoder and the two directions of each
+    CrossmodalTransformer pair on side streams (Engine::fork_to). Every kernel computes the same values whatever runs beside
+    it, so the logits must equal the single-stream forward (FMMT_NO_BRANCHES=1) bit for bit - eagerly and under graph replay,
+    repeatedly (a missing dependency or aliased scratch buffer shows up as a difference on some repetition)."""
+    from facialmmt_b200 import synthetic as syn
+    from facialmmt_b200.config import FmmtConfig, TextConfig
+    from facialmmt_b200.models import MultiModalTransformerForClassification
+    cfg = FmmtConfig(text=TextConfig.roberta_large(2))
+    sd = syn.multimodal_stress_state_dict(cfg, 1111)
+    U = 8
+    b = syn.synthetic_batch(cfg, U=U, L=128, seed=9, n_frames=[160] * U, with_faces=False)
+    dev = {k: (v.cuda() if torch.is_tensor(v) else v) for k, v in b.items()}
+    v519 = torch.cat([dev["vision"], torch.rand(U, dev["vision"].shape[1], cfg.fusion.num_labels, device="cuda")], dim=-1).contiguous()
+
+    def run(model):
+        return model(dev["text_ids"], dev["text_mask"], dev["sep_mask"], dev["audio"], dev["audio_mask"], v519,
+                     dev["vision_mask"], dev["idx_in_dia"]).clone()
+
+    monkeypatch.setenv("FMMT_NO_BRANCHES", "1")
+    single = MultiModalTransformerForClassification(cfg)
+    single.load_state_dict(sd)
+    ref = run(single)
+    single.check()
+    monkeypatch.delenv("FMMT_NO_BRANCHES")
+    par = MultiModalTransformerForClassification(cfg)
+    par.load_state_dict(sd)
+    for rep in range(20):
+        assert torch.equal(run(par), ref), f"eager repetition {rep}"
+    par.set_graph(True)
+    for rep in range(20):
+        assert torch.equal(run(par), ref), f"graph repetition {rep}"
+    par.check()
