@@ -304,6 +304,8 @@ struct FastParams {
   const float* ln_gamma;   // LayerNorm epilogue (fp32 output, N <= block_n, N % 32 == 0): out = LN(acc + bias) * gamma + beta;
   const float* ln_beta;    // one epilogue group owns a whole tile, so every thread sees all columns of its row
   float ln_eps;
+  int nacc, acc_stride;    // TMEM accumulator stages and their column stride (2 x 256; LayerNorm mode with N <= 128: 4 x 128,
+                           // one per epilogue group, so that all four groups normalise tiles concurrently)
 };
 
 template <int ACT>
@@ -338,8 +340,8 @@ gemm_bf16_tcgen05_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __gr
   extern __shared__ uint8_t smem_raw[];
   __shared__ uint64_t full_bar[MAX_STAGES];
   __shared__ uint64_t empty_bar[MAX_STAGES];
-  __shared__ uint64_t tmem_full_bar[2];
-  __shared__ uint64_t tmem_empty_bar[2];
+  __shared__ uint64_t tmem_full_bar[4];     // p.nacc accumulator stages (2, or 4 narrow ones in LayerNorm mode)
+  __shared__ uint64_t tmem_empty_bar[4];
   __shared__ uint64_t res_full_bar[RES_SLOTS];
   __shared__ uint64_t res_empty_bar[RES_SLOTS];
   __shared__ uint32_t tmem_base_slot;
@@ -359,7 +361,7 @@ gemm_bf16_tcgen05_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __gr
       mbar_init(&full_bar[s], 2);     // A producer + B producer, each with its own expect_tx
       mbar_init(&empty_bar[s], 1);
     }
-    for (int s = 0; s < 2; ++s) {
+    for (int s = 0; s < 4; ++s) {
       mbar_init(&tmem_full_bar[s], 1);
       mbar_init(&tmem_empty_bar[s], FAST_EPI_WARPS * 32);
     }
@@ -431,7 +433,7 @@ gemm_bf16_tcgen05_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __gr
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1u, 2);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * ACC_STRIDE);
+        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * p.acc_stride);
         for (int kb = 0; kb < p.num_kb; kb += KBS) {
           mbar_wait(&full_bar[stage], phase, 3);
           tc_fence_after();
@@ -451,7 +453,7 @@ gemm_bf16_tcgen05_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __gr
           if (++stage == p.num_stages) { stage = 0; phase ^= 1u; }
         }
         umma_commit(&tmem_full_bar[acc]);
-        acc ^= 1;
+        if (++acc == p.nacc) acc = 0;
         if (acc == 0) acc_phase ^= 1u;
       }
     }
@@ -495,7 +497,7 @@ gemm_bf16_tcgen05_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __gr
       mbar_wait(&tmem_full_bar[acc], acc_phase, 5);
       tc_fence_after();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) +
-                             static_cast<uint32_t>(acc * ACC_STRIDE);
+                             static_cast<uint32_t>(acc * p.acc_stride);
       // Slab with running number c = res_base + s goes to group c % EPI_GROUPS (== its residual-ring slot): work
       // rotates over the groups from tile to tile, and every group consumes EVERY use of "its" ring slot in order,
       // which is what makes the parity waits on res_full/res_empty alias-free.
@@ -558,7 +560,7 @@ gemm_bf16_tcgen05_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __gr
         res_base += 1u;   // LayerNorm mode: running TILE number of this CTA
         tc_fence_before();
         mbar_arrive(&tmem_empty_bar[acc]);
-        acc ^= 1;
+        if (++acc == p.nacc) acc = 0;
         if (acc == 0) acc_phase ^= 1u;
         continue;
       }
@@ -626,7 +628,7 @@ gemm_bf16_tcgen05_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __gr
       res_base += static_cast<uint32_t>(nsl);
       tc_fence_before();
       mbar_arrive(&tmem_empty_bar[acc]);
-      acc ^= 1;
+      if (++acc == p.nacc) acc = 0;
       if (acc == 0) acc_phase ^= 1u;
     }
     if (elected) tma_store_wait_all();
@@ -1442,6 +1444,8 @@ cudaError_t launch_gemm(const GemmArgs& a, cudaStream_t stream) {
     p.num_kb = (a.K + BK - 1) / BK;
     p.bias = a.bias; p.act = a.act;
     p.ln_gamma = a.ln_gamma; p.ln_beta = a.ln_beta; p.ln_eps = a.ln_eps;
+    p.nacc = 2; p.acc_stride = ACC_STRIDE;
+    if (a.ln_gamma != nullptr && p.block_n <= 128 && p.groups == EPI_GROUPS) { p.nacc = 4; p.acc_stride = 128; }
     if (a.ln_gamma != nullptr && (a.ln_beta == nullptr || p.n_tiles != 1 || p.out_bf16 || p.has_res || (a.N % 32) != 0 ||
                                   a.act != ACT_NONE))
       return cudaErrorInvalidValue;
