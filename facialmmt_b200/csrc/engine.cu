@@ -1181,7 +1181,8 @@ int Engine::swin_forward_u8(const uint8_t* crops, int F, int crop_h, int crop_w,
 cudaStream_t Engine::fork_to(int k) {
   cudaStream_t main_stream = st_;
   // (fp32-grade mode releases and re-uses scratch inside a branch, lin_to_operand: it stays on one stream)
-  if (!branches_ || precise_ || arena_.dry() || first_err_ != cudaSuccess) return main_stream;
+  // (the per-kernel event profile also runs on one stream: kernels timed beside each other would inflate one another)
+  if (!branches_ || precise_ || prof_ || arena_.dry() || first_err_ != cudaSuccess) return main_stream;
   if (side_[k] == nullptr) {
     ck(cudaStreamCreateWithFlags(&side_[k], cudaStreamNonBlocking), "side stream");
     ck(cudaEventCreateWithFlags(&ev_join_[k], cudaEventDisableTiming), "join event");
