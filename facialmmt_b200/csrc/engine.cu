@@ -1118,13 +1118,38 @@ void Engine::swin_body(const FrameSrc& frames, int F, const float* gumbel, float
   // round-2 build with the fused half-block kernels and graph replay (profiles/r02_chunk_sweep.txt): 64/1280 -> 242, 160/1280 -> 250,
   // 320/1280 -> 255, 640/1280 -> 258: L2-sized passes (64 frames = 77 MB of stage-1 residual) still lose to few large launches.
   // (fp32-grade mode keeps fp32 intermediates and split operands, 3-4x the bytes per frame: smaller passes)
-  const int big = c.swin_chunk_late > 0 ? c.swin_chunk_late : (precise_ ? 320 : 1280);
-  const int small = c.swin_chunk > 0 ? c.swin_chunk : (precise_ ? 80 : 640);
+  // Consecutive passes ALTERNATE BETWEEN TWO SIDE STREAMS (when there is more than one): every kernel of a pass is a
+  // persistent one-CTA-per-SM kernel whose last round leaves most SMs idle (stage 3: 980 tiles over 148 CTAs = 6.6 rounds),
+  // and the CTAs of the other pass's kernel start on exactly those SMs. Measured (U=8, 1280 frames): one 1280-frame pass 30.36 ms
+  // per step, two 640-frame passes on one stream 30.62, on two streams 29.59 (stage-1/2 sub-passes of 320).
+  // (the per-kernel event profile and the capture hooks keep the same pass sizes, on one stream)
+  const bool two_pass = branches_ && !precise_ && F > 640;
+  const bool can_branch = branches_ && !precise_ && !prof_ && caps_.empty();
+  const int big = c.swin_chunk_late > 0 ? c.swin_chunk_late : (precise_ ? 320 : (two_pass ? 640 : 1280));
+  const int small = c.swin_chunk > 0 ? c.swin_chunk : (precise_ ? 80 : (two_pass ? 320 : 640));
   const SwinStageW& ss = swin_.stages[split];
   const size_t per_frame_split = static_cast<size_t>(ss.R) * ss.R * ss.C;
-  for (int f0 = 0; f0 < F; f0 += big) {
+  const bool par = can_branch && F > big;
+  const size_t mark_all = arena_.mark();
+  size_t region[2] = {0, 0};
+  int it = 0;
+  for (int f0 = 0; f0 < F; f0 += big, ++it) {
     const int nb = std::min(big, F - f0);
     const size_t mark = arena_.mark();
+    cudaStream_t main_stream = st_;
+    if (par) {
+      // this pass runs beside the previous one. Passes 0 and 1 each get a region above everything allocated so far (the
+      // previous pass has released its scratch in the host-side bookkeeping only; its kernels are still in flight on the other
+      // stream); pass it >= 2 re-uses the region of pass it - 2 once that pass is complete (same size or smaller).
+      if (it < 2) {
+        arena_.release(arena_.peak());
+        region[it] = arena_.mark();
+      } else {
+        join_wait(it & 1);
+        arena_.release(region[it & 1]);
+      }
+      main_stream = fork_to(it & 1);
+    }
     float* x2 = arena_.alloc<float>(static_cast<size_t>(nb) * per_frame_split);
     for (int g0 = 0; g0 < nb; g0 += small) {
       const int ns = std::min(small, nb - g0);
@@ -1133,7 +1158,13 @@ void Engine::swin_body(const FrameSrc& frames, int F, const float* gumbel, float
       arena_.release(m2);
     }
     swin_late(x2, f0, nb, feat_ln);
-    arena_.release(mark);
+    if (par) branch_done(it & 1, main_stream);   // scratch stays reserved: the next pass runs beside this one
+    else arena_.release(mark);
+  }
+  if (par) {
+    join_wait(0);
+    join_wait(1);
+    arena_.release(mark_all);
   }
   GemmArgs g;                                                        // Linear(49*768, 512) with BatchNorm folded in
   g.out_f32 = feat512; g.ldo32 = c.feat_dim;

@@ -81,3 +81,32 @@ def test_parallel_branches_match_the_single_stream_forward(monkeypatch):
     for rep in range(20):
         assert torch.equal(run(par), ref), f"graph repetition {rep}"
     par.check()
+
+
+def test_alternating_swin_passes_match_the_single_stream_forward(monkeypatch):
+    """Consecutive Swin passes alternate between two side streams (Engine::swin_body) and re-use each other's arena regions
+    two passes later; the result must equal the single-stream forward bit for bit, eagerly and under graph replay."""
+    from facialmmt_b200 import synthetic as syn
+    from facialmmt_b200.config import FmmtConfig, TextConfig
+    from facialmmt_b200.models import SwinForAffwildClassification
+    cfg = FmmtConfig(text=TextConfig.roberta_large(2))
+    sd = syn.swin_cls_stress_state_dict(cfg.swin, 1111)
+    F = 23                                                        # passes of 5 frames: 5 passes, the last one ragged
+    g = torch.Generator().manual_seed(3)
+    frames = (torch.rand(F, 3, 224, 224, generator=g) * 2 - 1).cuda()
+    gum = -torch.log(torch.empty(F, 7).exponential_(generator=g)).cuda()
+    monkeypatch.setenv("FMMT_NO_BRANCHES", "1")
+    single = SwinForAffwildClassification(cfg, swin_chunk=3, swin_chunk_late=5)
+    single.load_state_dict(sd)
+    ref = [t.clone() for t in single.forward_full(frames, gum)]
+    single.check()
+    monkeypatch.delenv("FMMT_NO_BRANCHES")
+    par = SwinForAffwildClassification(cfg, swin_chunk=3, swin_chunk_late=5)
+    par.load_state_dict(sd)
+    for graph in (False, True):
+        par.set_graph(graph)
+        for rep in range(10):
+            out = par.forward_full(frames, gum)
+            for a, b in zip(out, ref):
+                assert torch.equal(a, b), f"graph={graph} repetition {rep}"
+    par.check()
