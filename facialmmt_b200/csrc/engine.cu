@@ -1123,10 +1123,13 @@ void Engine::swin_body(const FrameSrc& frames, int F, const float* gumbel, float
   // and the CTAs of the other pass's kernel start on exactly those SMs. Measured (U=8, 1280 frames): one 1280-frame pass 30.36 ms
   // per step, two 640-frame passes on one stream 30.62, on two streams 29.59 (stage-1/2 sub-passes of 320).
   // (the per-kernel event profile and the capture hooks keep the same pass sizes, on one stream)
-  const bool two_pass = branches_ && !precise_ && F > 640;
+  static const int min_two_pass = std::getenv("FMMT_TWO_PASS_MIN") ? atoi(std::getenv("FMMT_TWO_PASS_MIN")) : 160;
+  const bool two_pass = branches_ && !precise_ && F >= min_two_pass;
   const bool can_branch = branches_ && !precise_ && !prof_ && caps_.empty();
-  const int big = c.swin_chunk_late > 0 ? c.swin_chunk_late : (precise_ ? 320 : (two_pass ? 640 : 1280));
-  const int small = c.swin_chunk > 0 ? c.swin_chunk : (precise_ ? 80 : (two_pass ? 320 : 640));
+  int big2 = ((F + 1) / 2 + 7) / 8 * 8;          // two passes for small batches, passes of 640 for large ones
+  if (big2 > 640) big2 = 640;
+  const int big = c.swin_chunk_late > 0 ? c.swin_chunk_late : (precise_ ? 320 : (two_pass ? big2 : 1280));
+  const int small = c.swin_chunk > 0 ? c.swin_chunk : (precise_ ? 80 : (two_pass ? (big2 > 320 ? 320 : big2) : 640));
   const SwinStageW& ss = swin_.stages[split];
   const size_t per_frame_split = static_cast<size_t>(ss.R) * ss.R * ss.C;
   const bool par = can_branch && F > big;
