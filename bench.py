@@ -63,14 +63,12 @@ def ncu_traffic():
 
 
 def ncu_kernel_traffic(label):
-    """DRAM bytes of ONE launch of the kernel behind an event-profile label, from the `ncu --set full` capture of the same launch
-    geometry (profiles/r02_ncu_top_kernels.json)."""
+    """Mean DRAM bytes per launch of the kernel behind an event-profile label, from the committed ncu metric pass over one step
+    of this workload and launch geometry (profiles/r02_launches_final.json)."""
     want = next((v for k, v in LABEL_TO_NCU.items() if label.startswith(k)), None)
     try:
-        rows = [r for r in json.load(open(os.path.join(ROOT, "profiles", "r02_ncu_top_kernels.json"))) if r["kernel"] == want]
-        if not rows:
-            return None
-        return sum((r["dram_rd_MB"] + r["dram_wr_MB"]) * 1e6 for r in rows) / len(rows)
+        ks = [k for k in json.load(open(os.path.join(ROOT, "profiles", "r02_launches_final.json")))["kernels"] if k["kernel"] == want]
+        return ks[0]["dram_MB_per_launch"] * 1e6 if ks else None
     except Exception:
         return None
 
