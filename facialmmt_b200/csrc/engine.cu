@@ -518,6 +518,16 @@ int Engine::finalize() {
   cudaError_t e = cudaDeviceSynchronize();
   if (e != cudaSuccess) return set_error(FMMT_ERR_CUDA, std::string("fmmt_finalize: ") + cudaGetErrorString(e));
   cudaGetDevice(&device_);
+  {
+    // One device per PROCESS: the kernels' one-time setup (opt-in shared memory sizes, SM counts, resident-CTA counts) is
+    // cached per process for the device that was current first. A second device in the same process would launch without it,
+    // so it is refused here, with a message, instead of failing later (deployment model: one process per GPU under torchrun).
+    static std::atomic<int> g_process_device{-1};
+    int expected = -1;
+    if (!g_process_device.compare_exchange_strong(expected, device_) && expected != device_)
+      return set_error(FMMT_ERR_STATE, "fmmt_finalize: this process already drives CUDA device " + std::to_string(expected) +
+                                           "; libfacialmmt_b200 supports one device per process (run one process per GPU)");
+  }
   try {
     status_dev_ = dev_alloc<unsigned int>(1);
   } catch (const PackError& pe) {
